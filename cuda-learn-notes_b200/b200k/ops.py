@@ -1,0 +1,249 @@
+"""Tensor-level host wrappers over the C ABI (include/b200k.h).
+
+These are the single place where torch tensors are turned into raw pointers + sizes + the current CUDA stream.
+Argument checks reproduce the reference bindings' behaviour and error strings
+(kernels/hgemm/mma/basic/hgemm_mma_stage.cu:L2078-2087 CHECK_TORCH_TENSOR_DTYPE / _SHAPE,
+kernels/flash-attn/utils/utils.h:L66-78, kernels/flash-attn/mma/basic/flash_attn_mma_share_qkv.cu:L860).
+
+PyTorch is used for device memory and streams only; every computation happens in libb200k.so.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _loader as L
+
+_lib = L.lib
+
+_DTYPE_ENUM = {
+    torch.float32: L.F32,
+    torch.float16: L.F16,
+    torch.bfloat16: L.BF16,
+    torch.int8: L.I8,
+    torch.int32: L.I32,
+}
+if hasattr(torch, "float8_e4m3fn"):
+    _DTYPE_ENUM[torch.float8_e4m3fn] = L.FP8_E4M3
+    _DTYPE_ENUM[torch.float8_e5m2] = L.FP8_E5M2
+
+_TH_NAME = {
+    torch.float16: "torch::kHalf",
+    torch.float32: "torch::kFloat32",
+    torch.int32: "torch::kInt32",
+    torch.bfloat16: "torch::kBFloat16",
+    torch.int8: "torch::kInt8",
+}
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_dtype(t: torch.Tensor, dtype: torch.dtype) -> None:
+    if t.dtype != dtype:
+        # same message as the reference's CHECK_TORCH_TENSOR_DTYPE
+        raise RuntimeError("values must be " + _TH_NAME.get(dtype, str(dtype)))
+
+
+def _check_cuda_contig(*ts: torch.Tensor) -> None:
+    dev = None
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("b200k: tensors must live on a CUDA device (there is no CPU path)")
+        if not t.is_contiguous():
+            raise RuntimeError("b200k: tensors must be contiguous")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("b200k: tensors must be on the same device")
+
+
+class _DeviceGuard:
+    """The reference launches on whatever device is current; we launch on the tensors' device."""
+
+    def __init__(self, t: torch.Tensor):
+        self.dev = t.device
+
+    def __enter__(self):
+        self.ctx = torch.cuda.device(self.dev)
+        self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        return self.ctx.__exit__(*a)
+
+
+# ------------------------------------------------------------------------------------------------ HGEMM
+def hgemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, tn: bool = False, variant: int = L.HGEMM_AUTO) -> None:
+    """c[M,N] = a[M,K] @ B (in place).  ``b`` has logical shape [K,N]; for ``tn`` its storage is B^T row-major
+    (the reference's ``as_col_major``, kernels/hgemm/tools/utils.py:L135-140), i.e. it arrives as a [K,N]-shaped
+    view whose memory is [N,K] contiguous."""
+    _check_dtype(a, torch.float16)
+    _check_dtype(b, torch.float16)
+    _check_dtype(c, torch.float16)
+    M, K = a.size(0), a.size(1)
+    N = b.size(1)
+    if b.size(0) != K or c.size(0) != M or c.size(1) != N:
+        raise RuntimeError("Tensor size mismatch!")
+    if tn:
+        bt = b.t()  # [N,K]; must be the contiguous storage
+        _check_cuda_contig(a, bt, c)
+    else:
+        _check_cuda_contig(a, b, c)
+    with _DeviceGuard(a):
+        L.check(_lib.b200k_hgemm_f16(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, 1 if tn else 0, variant,
+                                     _stream(a)))
+
+
+# ------------------------------------------------------------------------------------------------ attention
+FA2_HEADDIMS = (32, 64, 96, 128)
+
+
+def _check_qkvo(q, k, v, o, v_is_dn=False):
+    for t in (q, k, v, o):
+        _check_dtype(t, torch.float16)
+    if q.dim() != 4:
+        raise RuntimeError("Tensor size mismatch!")
+    B, H, N, D = q.shape
+    vshape = (B, H, D, N) if v_is_dn else (B, H, N, D)
+    if tuple(k.shape) != (B, H, N, D) or tuple(v.shape) != vshape or tuple(o.shape) != (B, H, N, D):
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(q, k, v, o)
+    return B, H, N, D
+
+
+def fa2_fwd(q, k, v, o, scale: Optional[float] = None, v_is_dn: bool = False, variant: int = 0) -> None:
+    B, H, N, D = _check_qkvo(q, k, v, o, v_is_dn)
+    if D not in FA2_HEADDIMS:
+        raise RuntimeError("headdim not support!")
+    with _DeviceGuard(q):
+        L.check(_lib.b200k_fa2_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, D,
+                                       float(scale) if scale else 0.0, 1 if v_is_dn else 0, variant, _stream(q)))
+
+
+def ffpa_fwd(q, k, v, o, scale: Optional[float] = None, variant: int = 0) -> None:
+    B, H, N, D = _check_qkvo(q, k, v, o)
+    with _DeviceGuard(q):
+        rc = _lib.b200k_ffpa_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, D,
+                                     float(scale) if scale else 0.0, variant, _stream(q))
+    if rc == L.EHEADDIM:
+        raise RuntimeError("headdim not support!")
+    L.check(rc)
+
+
+# ------------------------------------------------------------------------------------------------ support kernels
+_ws_cache: dict = {}
+
+
+def _workspace(dev: torch.device) -> torch.Tensor:
+    key = (dev.type, dev.index)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.b200k_reduce_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
+def elementwise_add(a, b, c) -> None:
+    if a.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise RuntimeError("values must be torch::kFloat32 or torch::kHalf")
+    _check_dtype(b, a.dtype)
+    _check_dtype(c, a.dtype)
+    if a.numel() != b.numel() or a.numel() != c.numel():
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(a, b, c)
+    with _DeviceGuard(a):
+        L.check(_lib.b200k_elementwise_add(a.data_ptr(), b.data_ptr(), c.data_ptr(), a.numel(), _DTYPE_ENUM[a.dtype],
+                                           _stream(a)))
+
+
+def block_all_reduce_sum(x: torch.Tensor, acc_f16: bool = False) -> torch.Tensor:
+    """Returns a new 1-element tensor (f32, or i32 for int8 input) like the reference bindings
+    (kernels/reduce/block_all_reduce.cu:L734-760)."""
+    if x.dtype not in _DTYPE_ENUM or x.dtype == torch.int32:
+        raise RuntimeError("values must be a float/half/bfloat16/fp8/int8 tensor")
+    _check_cuda_contig(x)
+    out = torch.empty(1, dtype=torch.int32 if x.dtype == torch.int8 else torch.float32, device=x.device)
+    with _DeviceGuard(x):
+        L.check(_lib.b200k_block_all_reduce_sum(x.data_ptr(), out.data_ptr(), x.numel(), _DTYPE_ENUM[x.dtype],
+                                                1 if acc_f16 else 0, _workspace(x.device).data_ptr(), _stream(x)))
+    return out
+
+
+SOFTMAX_ALL, SOFTMAX_PER_TOKEN, SOFTMAX_SAFE, SOFTMAX_ONLINE = 0, 1, 2, 3
+
+
+def softmax(x, y, mode: int) -> None:
+    if x.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("values must be torch::kFloat32")
+    _check_dtype(y, x.dtype)
+    if x.shape != y.shape:
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(x, y)
+    if mode == SOFTMAX_ALL:
+        S, H = 1, x.numel()
+        # row kernels index columns with 32-bit ints: fold a long flat tensor into rows; the total is global anyway
+        if x.dim() >= 2:
+            S, H = x.numel() // x.size(-1), x.size(-1)
+    else:
+        S, H = x.numel() // x.size(-1), x.size(-1)
+    with _DeviceGuard(x):
+        L.check(_lib.b200k_softmax(x.data_ptr(), y.data_ptr(), S, H, _DTYPE_ENUM[x.dtype], mode,
+                                   _workspace(x.device).data_ptr(), _stream(x)))
+
+
+def rms_norm(x, y, g: float, eps: float = 1e-5, acc_f16: bool = False, eps_inside_k: bool = False) -> None:
+    if x.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("values must be torch::kFloat32")
+    _check_dtype(y, x.dtype)
+    if x.shape != y.shape or x.dim() != 2:
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(x, y)
+    with _DeviceGuard(x):
+        L.check(_lib.b200k_rms_norm(x.data_ptr(), y.data_ptr(), x.size(0), x.size(1), float(g), float(eps),
+                                    _DTYPE_ENUM[x.dtype], 1 if acc_f16 else 0, 1 if eps_inside_k else 0, _stream(x)))
+
+
+def rope_f32(x, out, ref_quirk: bool = True) -> None:
+    _check_dtype(x, torch.float32)
+    _check_dtype(out, torch.float32)
+    if x.shape != out.shape or x.dim() != 2:
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(x, out)
+    with _DeviceGuard(x):
+        L.check(_lib.b200k_rope_f32(x.data_ptr(), out.data_ptr(), x.size(0), x.size(1), 1 if ref_quirk else 0,
+                                    _stream(x)))
+
+
+def histogram_i32(a: torch.Tensor, nbins: Optional[int] = None) -> torch.Tensor:
+    """Returns int32 counts of length max(a)+1, like the reference (kernels/histogram/histogram.cu:L50-68), which
+    also reads max(a) back to the host to size its output."""
+    _check_dtype(a, torch.int32)
+    _check_cuda_contig(a)
+    with _DeviceGuard(a):
+        if nbins is None:
+            mx = torch.empty(1, dtype=torch.int32, device=a.device)
+            L.check(_lib.b200k_max_i32(a.data_ptr(), a.numel(), mx.data_ptr(), _stream(a)))
+            nbins = int(mx.item()) + 1
+        y = torch.empty(max(nbins, 1), dtype=torch.int32, device=a.device)
+        L.check(_lib.b200k_histogram_i32(a.data_ptr(), a.numel(), y.data_ptr(), y.numel(), _stream(a)))
+    return y
+
+
+def embedding(idx, weight, out) -> None:
+    _check_dtype(idx, torch.int32)
+    if weight.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise RuntimeError("values must be torch::kFloat32 or torch::kHalf")
+    _check_dtype(out, weight.dtype)
+    if weight.dim() != 2 or out.numel() != idx.numel() * weight.size(1):
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(idx, weight, out)
+    with _DeviceGuard(idx):
+        L.check(_lib.b200k_embedding(idx.data_ptr(), weight.data_ptr(), out.data_ptr(), idx.numel(), weight.size(0),
+                                     weight.size(1), _DTYPE_ENUM[weight.dtype], _stream(idx)))
+
+
+def default_scale(D: int) -> float:
+    return 1.0 / math.sqrt(D)

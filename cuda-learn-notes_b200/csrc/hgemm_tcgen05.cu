@@ -1,0 +1,329 @@
+// HGEMM for B200 (sm_100a): C[M,N] = A[M,K] * B, fp16 in/out, fp32 accumulate in tensor memory.
+//
+// One persistent, warp-specialised kernel:
+//   warp 0      TMA producer     cp.async.bulk.tensor 2-D loads of A and B k-blocks (64 wide) into a ring of
+//                                128B-swizzled smem stages, completion on "full" mbarriers
+//   warp 1      MMA issuer       one thread issues tcgen05.mma.kind::f16 (4 per k-block), tcgen05.commit releases the
+//                                smem stage ("empty" mbarrier) and, after the last k-block, publishes the accumulator
+//   warp 2      TMEM allocator   tcgen05.alloc / dealloc of 2 accumulator buffers (epilogue of tile i overlaps the
+//                                main loop of tile i+1)
+//   warps 4..7  epilogue         tcgen05.ld 32 lanes x 64 columns -> fp16 -> swizzled smem -> TMA store, per warp
+// CG = 2 pairs two CTAs (cta_group::2, cluster 2x1x1) on one 256 x BN tile: each CTA loads its 128 rows of A and
+// its half of B; the leader CTA issues the MMAs for both and multicasts the commits.
+//
+// This replaces the reference's cp.async + ldmatrix + mma.sync.m16n8k16 kernels
+//   kernels/hgemm/mma/basic/hgemm_mma_stage.cu:L590-1023 (kernel), L2380-2454 (launcher)  and their NN/TN siblings;
+// the reference's `stages`, `swizzle`, `swizzle_stride` arguments map onto the ring depth (fixed per variant), the
+// hardware 128B swizzle (always on) and the grouped tile rasterisation (GROUP_M) below.
+#include "abi_common.cuh"
+#include "ptx.cuh"
+
+namespace b200k {
+
+template <int CG_, int BN_, bool B_MN_, int STAGES_>
+struct GemmCfg {
+  static constexpr int CG = CG_;
+  static constexpr int BN = BN_;
+  static constexpr bool B_MN = B_MN_;  // true: B is [K,N] row-major (N contiguous) = "NN"; false: B^T [N,K] = "TN"
+  static constexpr int STAGES = STAGES_;
+  static constexpr int BM_CTA = 128;
+  static constexpr int BM = BM_CTA * CG;
+  static constexpr int BK = 64;
+  static constexpr int BN_CTA = BN / CG;  // rows of B (N index) each CTA stages
+  static constexpr int A_BYTES = BM_CTA * BK * 2;
+  static constexpr int B_BYTES = BN_CTA * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_WARP_BYTES = 2 * 32 * 128;  // two 32-row x 128-byte buffers per epilogue warp
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // two fp32 accumulator buffers
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + BAR_BYTES + STAGES * STAGE_BYTES + EPI_BYTES;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+  static_assert(BN_CTA % 64 == 0 && BN_CTA <= 256, "B box");
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+};
+
+// Grouped rasterisation: consecutive tile ids walk GROUP_M tile-rows down before moving one tile-column right, so
+// the ~74 tiles in flight share few A row-panels and few B column-panels (L2 reuse).  This is the B200 counterpart of
+// the reference's block-swizzle stride (hgemm_mma_stage.cu:L2339-2343, hgemm.py:L71-81).
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int* tm, int* tn) {
+  const int per_group = group_m * tiles_n;
+  const int g = t / per_group;
+  const int first_m = g * group_m;
+  const int gsz = min(group_m, tiles_m - first_m);
+  const int local = t - g * per_group;
+  *tm = first_m + local % gsz;
+  *tn = local / gsz;
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(256, 1)
+hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n,
+                     int group_m) {
+  constexpr int CG = Cfg::CG, BN = Cfg::BN, STAGES = Cfg::STAGES;
+  constexpr bool B_MN = Cfg::B_MN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+
+  const uint32_t bar_full = base;                  // STAGES x 8 B
+  const uint32_t bar_empty = base + 8 * STAGES;    // STAGES x 8 B
+  const uint32_t bar_tfull = base + 16 * STAGES;   // 2 x 8 B   accumulator ready   (MMA -> epilogue)
+  const uint32_t bar_tempty = bar_tfull + 16;      // 2 x 8 B   accumulator drained (epilogue -> MMA)
+  const uint32_t tmem_slot = bar_tempty + 16;      // 4 B
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
+  const uint32_t smem_tiles = base + Cfg::BAR_BYTES;
+  const uint32_t smem_epi = smem_tiles + STAGES * Cfg::STAGE_BYTES;
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
+  const int num_tiles = tiles_m * tiles_n;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4 * CG);  // one arrival per epilogue warp of every CTA in the pair
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane, both CTAs of a pair)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int tm, tn;
+        tile_coords(t, tiles_m, tiles_n, group_m, &tm, &tn);
+        const int m0 = tm * Cfg::BM + int(cta_rank) * Cfg::BM_CTA;
+        const int n0 = tn * BN + int(cta_rank) * Cfg::BN_CTA;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t fb_local = bar_full + 8 * stage;
+          const uint32_t sa = smem_tiles + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const int k0 = kb * Cfg::BK;
+          if constexpr (CG == 2) {
+            // all bytes of both CTAs are accounted on the leader's barrier
+            if (leader) mbar_arrive_expect_tx(fb_local, 2 * Cfg::STAGE_BYTES);
+            const uint32_t fb = mapa(fb_local, 0);
+            tma_load_2d_2sm(sa, &tmA, fb, k0, m0, kPolicyEvictNormal);
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int j = 0; j < Cfg::BN_CTA / 64; ++j)
+                tma_load_2d_2sm(sb + j * 8192, &tmB, fb, n0 + j * 64, k0, kPolicyEvictNormal);
+            } else {
+              tma_load_2d_2sm(sb, &tmB, fb, k0, n0, kPolicyEvictNormal);
+            }
+          } else {
+            mbar_arrive_expect_tx(fb_local, Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, fb_local, k0, m0, kPolicyEvictNormal);
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int j = 0; j < Cfg::BN_CTA / 64; ++j)
+                tma_load_2d(sb + j * 8192, &tmB, fb_local, n0 + j * 64, k0, kPolicyEvictNormal);
+            } else {
+              tma_load_2d(sb, &tmB, fb_local, k0, n0, kPolicyEvictNormal);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_f16(Cfg::BM, BN, /*acc_f32=*/true, /*a_mn=*/false, /*b_mn=*/B_MN);
+      // A: K-major, rows 128 B apart, 8-row groups 1024 B apart.
+      constexpr uint64_t a_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);
+      // B (TN): same K-major layout.  B (NN): MN-major, 64 N-elements per 128 B row, 8 K-rows per 1024 B atom (SBO),
+      // next 64 N-elements one TMA box (64 rows x 128 B = 8192 B) further (LBO).
+      constexpr uint64_t b_hi = B_MN ? make_smem_desc_hi(8192, 1024, kSwizzle128B) : make_smem_desc_hi(16, 1024, kSwizzle128B);
+      constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;  // bytes per UMMA_K = 16
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_tiles + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            const uint64_t adesc = smem_desc(a_hi, sa + k * 32);
+            const uint64_t bdesc = smem_desc(b_hi, sb + k * b_kstep);
+            umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (CG == 2) umma_commit_2sm(bar_empty + 8 * stage, 0b11);
+          else umma_commit(bar_empty + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (CG == 2) umma_commit_2sm(bar_tfull + 8 * acc, 0b11);
+        else umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> fp16 -> smem -> TMA store
+    const uint32_t q = warp & 3;  // TMEM lane quadrant this warp may read
+    const uint32_t epi = smem_epi + q * Cfg::EPI_WARP_BYTES;
+    uint32_t nbuf = 0;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      int tm, tn;
+      tile_coords(t, tiles_m, tiles_n, group_m, &tm, &tn);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row0 = tm * Cfg::BM + int(cta_rank) * Cfg::BM_CTA + int(q) * 32;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        uint32_t r[64];
+        const uint32_t taddr = tmem_addr(tmem_base, q * 32, acc * BN + c * 64);
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_32x32b_x32(taddr + 32, r + 32);
+        tmem_wait_ld();
+        if (c == BN / 64 - 1) {
+          // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(mapa(bar_tempty + 8 * acc, 0));
+            else mbar_arrive(bar_tempty + 8 * acc);
+          }
+        }
+        const uint32_t buf = epi + (nbuf & 1) * 4096;
+        ++nbuf;
+        if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+        __syncwarp();
+        const uint32_t row_addr = buf + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float* f = reinterpret_cast<const float*>(r + 8 * j);
+          st_shared_v4(row_addr + ((j ^ (lane & 7)) << 4), pack_half2(f[0], f[1]), pack_half2(f[2], f[3]),
+                       pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int col0 = tn * BN + c * 64;
+        if (lane == 0 && row0 < M && col0 < N) {
+          tma_store_2d(&tmC, buf, col0, row0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <class Cfg>
+static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
+                        const DeviceInfo& di) {
+  CUtensorMap tmA, tmB, tmC;
+  int rc;
+  if ((rc = make_tmap_2d_u16(&tmA, A, M, K, K, Cfg::BM_CTA, Cfg::BK, true))) return rc;
+  if (Cfg::B_MN) rc = make_tmap_2d_u16(&tmB, B, K, N, N, Cfg::BK, 64, true);
+  else rc = make_tmap_2d_u16(&tmB, B, N, K, K, Cfg::BN_CTA, Cfg::BK, true);
+  if (rc) return rc;
+  if ((rc = make_tmap_2d_u16(&tmC, C, M, N, N, 32, 64, true))) return rc;
+
+  const int tiles_m = int((M + Cfg::BM - 1) / Cfg::BM);
+  const int tiles_n = int((N + Cfg::BN - 1) / Cfg::BN);
+  const int64_t num_tiles = int64_t(tiles_m) * tiles_n;
+  const int max_clusters = di.sm_count / Cfg::CG;
+  const int clusters = int(num_tiles < max_clusters ? num_tiles : max_clusters);
+  const int group_m = 8;
+
+  auto kern = hgemm_tcgen05_kernel<Cfg>;
+  static bool attr_set[64] = {};
+  if (!attr_set[di.device]) {
+    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[di.device] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * Cfg::CG);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = Cfg::CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, int(M), int(N), int(K), tiles_m, tiles_n, group_m));
+  return B200K_OK;
+}
+
+}  // namespace b200k
+
+extern "C" int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk,
+                               int variant, void* stream) {
+  using namespace b200k;
+  if (!A || !B || !C) return set_error(B200K_EARG, "b200k_hgemm_f16: null pointer");
+  if (M < 1 || N < 1 || K < 1 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
+    return set_error(B200K_ESHAPE, "b200k_hgemm_f16: M,N,K must be in [1, 2^31) (got %lld,%lld,%lld)", (long long)M,
+                     (long long)N, (long long)K);
+  if ((K % 8) || (N % 8))
+    return set_error(B200K_ESHAPE, "b200k_hgemm_f16: K and N must be multiples of 8 (16-byte rows), got K=%lld N=%lld",
+                     (long long)K, (long long)N);
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (variant == B200K_HGEMM_AUTO) {
+    // 256x256 pair tiles when they fill the machine; the narrower pair tile for small problems.
+    const int64_t t256 = ((M + 255) / 256) * ((N + 255) / 256);
+    variant = (t256 >= (di.sm_count / 2)) ? B200K_HGEMM_2CTA_256x256 : B200K_HGEMM_2CTA_256x128;
+  }
+  const bool nn = (b_is_nk == 0);
+  switch (variant) {
+    case B200K_HGEMM_1CTA_128x256:
+      return nn ? launch_hgemm<GemmCfg<1, 256, true, 4>>(A, B, C, M, N, K, s, di)
+                : launch_hgemm<GemmCfg<1, 256, false, 4>>(A, B, C, M, N, K, s, di);
+    case B200K_HGEMM_2CTA_256x256:
+      return nn ? launch_hgemm<GemmCfg<2, 256, true, 6>>(A, B, C, M, N, K, s, di)
+                : launch_hgemm<GemmCfg<2, 256, false, 6>>(A, B, C, M, N, K, s, di);
+    case B200K_HGEMM_2CTA_256x128:
+      return nn ? launch_hgemm<GemmCfg<2, 128, true, 8>>(A, B, C, M, N, K, s, di)
+                : launch_hgemm<GemmCfg<2, 128, false, 8>>(A, B, C, M, N, K, s, di);
+    default:
+      return set_error(B200K_EARG, "b200k_hgemm_f16: unknown variant %d", variant);
+  }
+}
