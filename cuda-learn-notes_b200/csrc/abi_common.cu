@@ -83,7 +83,7 @@ int make_tmap_2d_u16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 }
 
 int make_tmap_3d_u16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint64_t stride2,
-                     uint64_t stride1, uint32_t box2, uint32_t box1, uint32_t box0, bool swizzle128) {
+                     uint64_t stride1, uint32_t box2, uint32_t box1, uint32_t box0, int swizzle_bytes) {
   EncodeTiledFn fn;
   int rc = get_encode_fn(&fn);
   if (rc) return rc;
@@ -94,7 +94,11 @@ int make_tmap_3d_u16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d
   cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                        : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(B200K_ECUDA, "cuTensorMapEncodeTiled(3d %llux%llux%llu box=%ux%ux%u) failed with CUresult %d",
