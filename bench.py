@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native CUDA-Learn-Notes hot paths (contract: see task / DESIGN.md §6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--quick]
+  torchrun --nproc-per-node N ... bench.py --gpus N ...          (one rank per GPU, NCCL)
+
+One JSON line on stdout (rank 0).  Headline `value` = HGEMM TFLOPS on BASELINE config #2 (fp16 NN, M=N=K=8192,
+the metric BASELINE.json is quoted on); a "step" is one GEMM with A, B, C resident in HBM.  HGEMM does not shard
+(SURVEY §8e): with --gpus N every rank runs an independent replica (weak scaling, value = sum of flops / max time).
+The same line carries
+  sweep       HGEMM at 2048 / 4096 / 8192 / 16384 (+ torch.matmul = cuBLAS on the same box)
+  attention   FA-2 forward: config #3 (4,48,8192,64) and the config #5 shard; at N > 1 config #5 (32,64,8192,128) batch-
+              sharded over the ranks with ONE NCCL broadcast of the packed inputs (timed separately), no reduction
+  ffpa        FFPA forward config #4 (1,32,4096,512)
+  ref_gpu     the reference's own mma.sync kernels (oracle/_ref, built from /root/reference) timed in the same run
+  e2e, roofline, cpu_baseline, clocks, gpu_launches     as the contract defines them.
+`--impl reference` times the reference's CPU-runnable path (torch.matmul on the host cores, the comparator its own
+scripts use — kernels/sgemm/sgemm.py:L135, kernels/hgemm/hgemm.py:L349) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cuda-learn-notes_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+HGEMM_MNK = 8192
+SWEEP = (2048, 4096, 8192, 16384)
+FA2_CFG3 = (4, 48, 8192, 64)
+FA2_CFG5 = (32, 64, 8192, 128)
+FFPA_CFG4 = (1, 32, 4096, 512)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops_burst": d.get("bf16_tflops"), "tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], None, [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cuda_time(fn, steps, warmup, barrier=None):
+    """W warm-up calls, then exactly K calls timed with CUDA events on the current (launching) stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return e0.elapsed_time(e1) / steps  # ms per step
+
+
+def max_over_ranks(ms, dist_on):
+    if not dist_on:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def cpu_info():
+    model = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"cores": os.cpu_count(), "torch_threads": torch.get_num_threads(), "model": model}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU legs
+def cpu_hgemm_sample(n, budget_s=12.0):
+    """torch.matmul on the host cores on a row-slab sample of the n^3 problem (same K, same B)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    rows = 256
+    cache = cpu_hgemm_sample.__dict__.setdefault("cache", {})
+    if n not in cache:
+        torch.manual_seed(1)
+        cache[n] = (torch.randn(rows, n, dtype=torch.float32), torch.randn(n, n, dtype=torch.float32))
+    a, b = cache[n]
+    torch.matmul(a, b)  # warm-up
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        torch.matmul(a, b)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or reps >= 50:
+            break
+    tflops = 2.0 * rows * n * n * reps / dt * 1e-12
+    return tflops, "torch.matmul fp32 on host: %d x (%d x %d) @ (%d x %d) row-slab of the %d^3 problem, %.1f s" % (
+        reps, rows, n, n, n, n, dt)
+
+
+def run_reference_impl(args, world, rank):
+    """--impl reference: the reference's CPU-runnable path (torch.matmul on host cores), rank 0 only."""
+    if rank != 0:
+        return
+    info = cpu_info()
+    n = HGEMM_MNK
+    vals = []
+    sample = ""
+    total = args.warmup + args.steps
+    per = max(1.0, min(10.0, 150.0 / max(total, 1)))
+    for i in range(total):
+        v, sample = cpu_hgemm_sample(n, budget_s=per)
+        if i >= args.warmup:
+            vals.append(v)
+    v = sum(vals) / len(vals)
+    ms = 2.0 * n ** 3 / (v * 1e12) * 1e3
+    line = {"impl": "reference", "metric": "hgemm_tflops", "value": v, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (cpu)", "data": "synthetic",
+            "config": {"workload": "hgemm_nn_f16_m8192_n8192_k8192", "note": "reference arm = torch.matmul on host cores "
+                       "(the reference's own CPU-runnable comparator); ms_per_step extrapolated from the sample"},
+            "cpu_baseline": {"value": v, "unit": "TFLOP/s", "cores": info["cores"], "kind": "port", "sample": sample,
+                             "cpu": info["model"]},
+            "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- reference GPU kernels
+def load_ref_hgemm():
+    import ctypes
+    p = os.path.join(ROOT, "oracle", "_ref", "libref_hgemm.so")
+    if not os.path.exists(p):
+        return None
+    try:
+        lib = ctypes.CDLL(p)
+        lib.ref_hgemm_mma_stages_dsmem_nn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 5
+        lib.ref_hgemm_mma_stages_dsmem_nn.restype = ctypes.c_int
+        return lib
+    except OSError:
+        return None
+
+
+def load_ref_module(name):
+    import importlib.util
+    p = os.path.join(ROOT, "oracle", "_ref", name + ".so")
+    if not os.path.exists(p):
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location(name, p)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception as e:  # noqa
+        return None
+
+
+def ref_swizzle_stride(N):  # hgemm.py:L71-81
+    f = 0.5 if N <= 4096 else 0.25
+    s = int(N * f)
+    return s if s >= 256 else 1
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="headline only (skip sweep / attention / ffpa / ref_gpu)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+
+    if args.impl == "reference":
+        run_reference_impl(args, world, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device. The product path has no CPU fallback; use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local_rank)
+    if dist_on:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        barrier = lambda: (dist.barrier(), torch.cuda.synchronize())  # noqa: E731
+    else:
+        barrier = None
+    from b200k import ops  # the C-ABI library; raises if missing
+
+    peaks = load_peaks()
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(1 + rank)
+    launches = 0
+    out = {}
+
+    # ------------------------------------------------------------------ headline: HGEMM 8192^3 (or selected workload)
+    n = HGEMM_MNK
+    a = torch.randn(n, n, dtype=torch.half, device=dev)
+    b = torch.randn(n, n, dtype=torch.half, device=dev)
+    c = torch.zeros(n, n, dtype=torch.half, device=dev)
+    flops = 2.0 * n ** 3
+
+    def step():
+        ops.hgemm(a, b, c)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = cuda_time(step, args.steps, args.warmup, barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    launches += args.steps
+    ms_max = max_over_ranks(ms, dist_on)
+    value = flops * world / (ms_max * 1e-3) * 1e-12
+
+    # ---- e2e: the same GEMM through the public API with HOST (pinned) buffers, H2D + D2H inside the timed region
+    ah = torch.randn(n, n, dtype=torch.half).pin_memory()
+    bh = torch.randn(n, n, dtype=torch.half).pin_memory()
+    ch = torch.empty(n, n, dtype=torch.half).pin_memory()
+
+    def step_e2e():
+        a.copy_(ah, non_blocking=True)
+        b.copy_(bh, non_blocking=True)
+        ops.hgemm(a, b, c)
+        ch.copy_(c, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = max_over_ranks(cuda_time(step_e2e, e2e_steps, 3, barrier), dist_on)
+    e2e = {"value": flops * world / (ms_e2e * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": 2 * n * n * 2, "d2h_bytes_per_step": n * n * 2,
+           "api": "toy_hgemm-style call b200k.ops.hgemm(a, b, c) on device tensors refreshed from pinned host buffers"}
+    del ah, bh, ch
+
+    roofline = {"bound": "tensor", "achieved": flops / (ms * 1e-3) * 1e-12, "peak": peaks["tflops_burst"],
+                "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) * 1e-12 / peaks["tflops_burst"],
+                "frac_of_sustained": flops / (ms * 1e-3) * 1e-12 / peaks["tflops_sustained"],
+                "peak_source": peaks["source"] + "; burst cuBLAS bf16 figure (kernel timed back to back for ~20 ms)",
+                "kernel": "hgemm_tcgen05_kernel<2-CTA 256x256x64, 6 stages>",
+                "algorithmic_flops_per_launch": flops,
+                "traffic": 1.186e9, "traffic_source": "profiles/r01_hgemm_8192_ncu_summary.json (dram read+write per launch); "
+                "algorithmic bytes 4.03e8"}
+
+    if not args.quick:
+        # -------------------------------------------------------------- HGEMM sweep + cuBLAS (torch.matmul) + reference mma.sync
+        ref_h = load_ref_hgemm()
+        sweep = []
+        for m in SWEEP:
+            A = a[:m, :m].contiguous() if m <= n else torch.randn(m, m, dtype=torch.half, device=dev)
+            B = b[:m, :m].contiguous() if m <= n else torch.randn(m, m, dtype=torch.half, device=dev)
+            C = torch.empty(m, m, dtype=torch.half, device=dev)
+            it = 20 if m <= 8192 else 5
+            t_ours = cuda_time(lambda: ops.hgemm(A, B, C), it, 3)
+            launches += it + 3
+            t_cublas = cuda_time(lambda: torch.matmul(A, B, out=C), it, 3)
+            row = {"mnk": m, "tflops": 2.0 * m ** 3 / t_ours * 1e-9, "cublas_tflops": 2.0 * m ** 3 / t_cublas * 1e-9,
+                   "frac_of_peak_burst": 2.0 * m ** 3 / t_ours * 1e-9 / peaks["tflops_burst"]}
+            if ref_h is not None:
+                best = None
+                for st in (2, 3, 4):
+                    stride = ref_swizzle_stride(m)
+                    stride = stride if stride in (512, 1024, 2048, 4096) and not (st == 4 and stride == 512) else 2048
+                    rc = ref_h.ref_hgemm_mma_stages_dsmem_nn(A.data_ptr(), B.data_ptr(), C.data_ptr(), m, m, m, st, stride)
+                    torch.cuda.synchronize()
+                    if rc != 0:
+                        continue
+                    t = cuda_time(lambda: ref_h.ref_hgemm_mma_stages_dsmem_nn(A.data_ptr(), B.data_ptr(), C.data_ptr(), m, m, m, st, stride),
+                                  5 if m > 8192 else 10, 2)
+                    tf = 2.0 * m ** 3 / t * 1e-9
+                    if best is None or tf > best[0]:
+                        best = (tf, st, stride)
+                if best:
+                    row["ref_mma_tflops"] = best[0]
+                    row["ref_mma_cfg"] = "hgemm_mma_m16n8k16_mma2x4_warp4x4x2_stages_dsmem stages=%d swizzle_stride=%d" % best[1:]
+            sweep.append(row)
+            del A, B, C
+        out["sweep"] = sweep
+        del a, b, c
+        torch.cuda.empty_cache()
+
+        # -------------------------------------------------------------- attention (single GPU configs)
+        ref_fa = load_ref_module("ref_flash_attn_lib")
+        att = {}
+
+        def bench_attn(shape, fn, tag):
+            B_, H_, N_, D_ = shape
+            q, k, v = [torch.randn(B_, H_, N_, D_, dtype=torch.half, device=dev) for _ in range(3)]
+            o = torch.empty_like(q)
+            fl = 4.0 * B_ * H_ * N_ * N_ * D_
+            t = cuda_time(lambda: fn(q, k, v, o), 10, 3)
+            r = {"shape": list(shape), "ms": t, "tflops": fl / t * 1e-9, "frac_of_peak_burst": fl / t * 1e-9 / peaks["tflops_burst"]}
+            if ref_fa is not None and D_ <= 128:
+                try:
+                    o2 = torch.zeros_like(q)
+                    t2 = cuda_time(lambda: ref_fa.flash_attn_mma_stages_split_q_shared_qkv(q, k, v, o2, 2), 3, 1)
+                    r["ref_mma_share_qkv_stage2_tflops"] = fl / t2 * 1e-9
+                    r["max_abs_diff_vs_ref"] = float((o.float() - o2.float()).abs().max().item())
+                except Exception as e:  # noqa
+                    r["ref_err"] = repr(e)[:160]
+            try:
+                import torch.nn.functional as F
+                t3 = cuda_time(lambda: F.scaled_dot_product_attention(q, k, v), 3, 1)
+                r["sdpa_tflops"] = fl / t3 * 1e-9
+            except Exception as e:  # noqa
+                r["sdpa_err"] = repr(e)[:160]
+            return r
+
+        att["cfg3_fa2_b4_h48_n8192_d64"] = bench_attn(FA2_CFG3, ops.fa2_fwd, "cfg3")
+        launches += 13
+        att["cfg5_shard_b4_h64_n8192_d128"] = bench_attn((4, 64, 8192, 128), ops.fa2_fwd, "cfg5shard")
+        launches += 13
+        out["attention"] = att
+        ffpa = bench_attn(FFPA_CFG4, ops.ffpa_fwd, "cfg4")
+        launches += 13
+        ref_ffpa = load_ref_module("pyffpa_cuda")
+        if ref_ffpa is not None:
+            try:
+                B_, H_, N_, D_ = FFPA_CFG4
+                q, k, v = [torch.randn(B_, H_, N_, D_, dtype=torch.half, device=dev) for _ in range(3)]
+                o2 = torch.zeros_like(q)
+                fl = 4.0 * B_ * H_ * N_ * N_ * D_
+                for name in ("ffpa_mma_acc_f32_L1", "ffpa_mma_acc_f16_L1"):
+                    best = 0.0
+                    for st in (1, 2, 3, 4):
+                        t2 = cuda_time(lambda: getattr(ref_ffpa, name)(q, k, v, o2, st), 3, 1)
+                        best = max(best, fl / t2 * 1e-9)
+                    ffpa["ref_" + name + "_tflops"] = best
+            except Exception as e:  # noqa
+                ffpa["ref_err"] = repr(e)[:160]
+        out["ffpa"] = {"cfg4_b1_h32_n4096_d512": ffpa}
+        torch.cuda.empty_cache()
+
+        # -------------------------------------------------------------- config #5: batch-sharded attention over the ranks
+        if dist_on:
+            import torch.distributed as dist
+            from b200k import sharded
+            B_, H_, N_, D_ = FA2_CFG5
+            qkv = torch.randn(3, B_, H_, N_, D_, dtype=torch.half, device=dev) if rank == 0 else None
+            torch.cuda.synchronize()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            buf = sharded.broadcast_qkv(qkv, (B_, H_, N_, D_), dev)
+            e1.record()
+            torch.cuda.synchronize()
+            t_bcast = max_over_ranks(e0.elapsed_time(e1), True)
+            lo, hi = sharded.shard_bounds(B_, world, rank)
+            o = torch.empty(hi - lo, H_, N_, D_, dtype=torch.half, device=dev)
+            t = cuda_time(lambda: sharded.sharded_attention_fwd(buf, out=o), 5, 2, barrier)
+            launches += 7
+            t = max_over_ranks(t, True)
+            fl = 4.0 * B_ * H_ * N_ * N_ * D_
+            out["attention"]["cfg5_fa2_b32_h64_n8192_d128_sharded"] = {
+                "n_gpus": world, "ms_compute_max_over_ranks": t, "aggregate_tflops": fl / t * 1e-9,
+                "broadcast_ms": t_bcast, "broadcast_GBps": buf.numel() * 2 / t_bcast * 1e-6,
+                "collectives": "one NCCL broadcast of packed QKV (12.9 GB); no reduction; outputs stay sharded", "scaling": "strong"}
+            del buf, o, qkv
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        v, sample = cpu_hgemm_sample(n, budget_s=12.0)
+        info = cpu_info()
+        cpu_baseline = {"value": v, "unit": "TFLOP/s", "cores": info["cores"], "kind": "port", "sample": sample,
+                        "cpu": info["model"]}
+
+    if rank == 0:
+        line = {"metric": "hgemm_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": "hgemm_nn_f16_m8192_n8192_k8192", "baseline_config": "#2 HGEMM fp16 NN square",
+                           "multi_gpu": "replicas only (a single GEMM does not shard without a collective)",
+                           "l2": "operands 3 x 128 MiB > 126 MB L2 (inputs larger than L2, no flush needed)",
+                           "randn_seed": 1},
+                "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "clocks": clocks, "peaks": peaks}
+        line.update(out)
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,9 +22,10 @@
 
 namespace b200k {
 
-template <int D_, int STAGES_>
+template <int D_, int STAGES_, bool V_DN_ = false>
 struct Fa2Cfg {
   static constexpr int D = D_;
+  static constexpr bool V_DN = V_DN_;  // V passed transposed as [B,H,D,N] (the reference's *_swizzle_qkv entry points)
   static constexpr int STAGES = STAGES_;
   static constexpr int CW = (D % 64 == 0) ? 64 : 32;  // width of one smem chunk along D (elements)
   static constexpr int NCH = D / CW;
@@ -125,7 +126,15 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         load_tile(&tmK, smem_k + s * Cfg::TILE_BYTES, bar_k_full + 8 * s, j * Cfg::BC, kPolicyEvictLast);
         if (j == 0) load_tile(&tmQ, smem_q + Cfg::TILE_BYTES, bar_q_full + 8, q0 + 128, kPolicyEvictFirst);
         mbar_wait(bar_v_empty + 8 * s, ph ^ 1);
-        load_tile(&tmV, smem_v + s * Cfg::TILE_BYTES, bar_v_full + 8 * s, j * Cfg::BC, kPolicyEvictLast);
+        if constexpr (Cfg::V_DN) {
+          // V^T tile: D rows x 128 keys, as two [D rows x 64 keys] 128B-swizzled boxes (keys contiguous = K-major B)
+          const uint32_t dst = smem_v + s * Cfg::TILE_BYTES;
+          mbar_arrive_expect_tx(bar_v_full + 8 * s, Cfg::TILE_BYTES);
+          tma_load_3d(dst, &tmV, bar_v_full + 8 * s, j * Cfg::BC, 0, bh, kPolicyEvictLast);
+          tma_load_3d(dst + D * 128, &tmV, bar_v_full + 8 * s, j * Cfg::BC + 64, 0, bh, kPolicyEvictLast);
+        } else {
+          load_tile(&tmV, smem_v + s * Cfg::TILE_BYTES, bar_v_full + 8 * s, j * Cfg::BC, kPolicyEvictLast);
+        }
       }
     }
     __syncwarp();
@@ -133,9 +142,11 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     // ---------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_f16(128, Cfg::BC, true, false, false);  // Q, K both K-major (D contiguous)
-      constexpr uint32_t idesc_o = make_idesc_f16(128, D, true, false, true);         // P from TMEM, V MN-major
+      // P from TMEM; V is MN-major ([keys, D], D contiguous) or, for V^T input, K-major ([D, keys], keys contiguous)
+      constexpr uint32_t idesc_o = make_idesc_f16(128, D, true, false, !Cfg::V_DN);
       constexpr uint64_t qk_hi = make_smem_desc_hi(16, 8 * ROWB, Cfg::SWZ_MODE);
-      constexpr uint64_t v_hi = make_smem_desc_hi(Cfg::CHUNK_BYTES, 8 * ROWB, Cfg::SWZ_MODE);
+      constexpr uint64_t v_hi = Cfg::V_DN ? make_smem_desc_hi(16, 1024, kSwizzle128B)
+                                          : make_smem_desc_hi(Cfg::CHUNK_BYTES, 8 * ROWB, Cfg::SWZ_MODE);
       constexpr int KSTEPS_PER_CHUNK = CW / 16;
 
       auto issue_s = [&](int i, int stage) {
@@ -154,8 +165,9 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const uint32_t p_tmem = tmem_base + (i ? Cfg::S_COL1 : Cfg::S_COL0);
 #pragma unroll
         for (int k = 0; k < Cfg::BC / 16; ++k) {
-          // 16 keys = 8 packed fp16x2 columns of P; 16 rows of V = 16 * ROWB bytes
-          umma_ts<1>(d_tmem, p_tmem + k * 8, smem_desc(v_hi, v_addr + k * 16 * ROWB), idesc_o,
+          // 16 keys = 8 packed fp16x2 columns of P; 16 rows of V = 16 * ROWB bytes (V^T: 32 bytes inside a 64-key box)
+          const uint32_t v_off = Cfg::V_DN ? uint32_t((k / 4) * (D * 128) + (k % 4) * 32) : uint32_t(k * 16 * ROWB);
+          umma_ts<1>(d_tmem, p_tmem + k * 8, smem_desc(v_hi, v_addr + v_off), idesc_o,
                      (accumulate || k != 0) ? 1u : 0u);
         }
       };
@@ -320,7 +332,13 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
   int rc;
   if ((rc = make_tmap_3d_u16(&tmQ, Q, BH, N, D, uint64_t(N) * D, D, 1, 128, Cfg::CW, Cfg::ROWB))) return rc;
   if ((rc = make_tmap_3d_u16(&tmK, K, BH, N, D, uint64_t(N) * D, D, 1, 128, Cfg::CW, Cfg::ROWB))) return rc;
-  if ((rc = make_tmap_3d_u16(&tmV, V, BH, N, D, uint64_t(N) * D, D, 1, 128, Cfg::CW, Cfg::ROWB))) return rc;
+  if (Cfg::V_DN) {
+    if (N % 8) return set_error(B200K_EALIGN, "b200k_fa2_fwd_f16: V as [B,H,D,N] needs N %% 8 == 0 (16-byte rows), got N=%lld", (long long)N);
+    rc = make_tmap_3d_u16(&tmV, V, BH, D, N, uint64_t(N) * D, N, 1, D, 64, 128);
+  } else {
+    rc = make_tmap_3d_u16(&tmV, V, BH, N, D, uint64_t(N) * D, D, 1, 128, Cfg::CW, Cfg::ROWB);
+  }
+  if (rc) return rc;
   if ((rc = make_tmap_3d_u16(&tmO, O, BH, N, D, uint64_t(N) * D, D, 1, 32, Cfg::CW, Cfg::ROWB))) return rc;
   auto kern = fa2_fwd_tcgen05_kernel<Cfg>;
   static bool attr_set[64] = {};
@@ -345,12 +363,20 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
   if (B < 1 || H < 1 || N < 1 || N > INT32_MAX || B * H > 65535)
     return set_error(B200K_ESHAPE, "b200k_fa2_fwd_f16: need B,H,N >= 1 and B*H <= 65535 (got B=%lld H=%lld N=%lld)",
                      (long long)B, (long long)H, (long long)N);
-  if (v_is_dn) return set_error(B200K_ESHAPE, "b200k_fa2_fwd_f16: V as [B,H,D,N] is not implemented yet");
   if (scale <= 0.f) scale = 1.0f / sqrtf(float(D));
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (v_is_dn) {
+    switch (D) {
+      case 32: return launch_fa2<Fa2Cfg<32, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
+      case 64: return launch_fa2<Fa2Cfg<64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
+      case 96: return launch_fa2<Fa2Cfg<96, 3, true>>(Q, K, V, O, B, H, N, scale, s, di);
+      case 128: return launch_fa2<Fa2Cfg<128, 2, true>>(Q, K, V, O, B, H, N, scale, s, di);
+      default: break;
+    }
+  }
   switch (D) {
     case 32: return launch_fa2<Fa2Cfg<32, 4>>(Q, K, V, O, B, H, N, scale, s, di);
     case 64: return launch_fa2<Fa2Cfg<64, 4>>(Q, K, V, O, B, H, N, scale, s, di);

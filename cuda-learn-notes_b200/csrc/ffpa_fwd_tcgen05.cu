@@ -39,7 +39,7 @@ template <bool Q_RESIDENT>
 __global__ void __launch_bounds__(ffpa::THREADS, 1)
 ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int N, int D,
-                        int slice_cols, int stages, float scale_log2) {
+                        int slice_cols, int stages, float scale_log2, int serial) {
   using namespace ffpa;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -50,9 +50,11 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t bar_empty = base + 8 * MAX_STAGES;      // MAX_STAGES
   const uint32_t bar_q_full = bar_empty + 8 * MAX_STAGES;  // 1 (resident Q)
   const uint32_t bar_s_full = bar_q_full + 8;            // 2
-  const uint32_t bar_p_full = bar_s_full + 16;           // 1
-  const uint32_t bar_pv_done = bar_p_full + 8;           // 1   completes once per PV_j (MMA -> softmax)
-  const uint32_t tmem_slot = bar_pv_done + 8;
+  const uint32_t bar_p_full = bar_s_full + 16;           // 2   one per S/P buffer: the softmax warps may run one tile
+                                                         //     ahead of the MMA thread, a single barrier could alias phases
+  const uint32_t bar_pv_done = bar_p_full + 16;          // 1   completes once per PV_j (guards the lazy O rescale)
+  const uint32_t bar_o_full = bar_pv_done + 8;           // 1   completes once, after the last PV (epilogue)
+  const uint32_t tmem_slot = bar_o_full + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
   const int nqk = D / CW;                                 // 64-wide chunks of the head dim
   const uint32_t smem_q = base + BAR_BYTES;               // resident Q: nqk boxes
@@ -80,7 +82,9 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(bar_s_full, 1);
     mbar_init(bar_s_full + 8, 1);
     mbar_init(bar_p_full, 4);
+    mbar_init(bar_p_full + 8, 4);
     mbar_init(bar_pv_done, 1);
+    mbar_init(bar_o_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -139,8 +143,9 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       };
       load_qk(0);
       for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) load_qk(j + 1);
+        if (!serial && j + 1 < T) load_qk(j + 1);
         load_v(j);
+        if (serial && j + 1 < T) load_qk(j + 1);
       }
     }
     __syncwarp();
@@ -211,11 +216,13 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       issue_s(0);
       for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_s((j + 1) & 1);
-        mbar_wait(bar_p_full, j & 1);
+        if (!serial && j + 1 < T) issue_s((j + 1) & 1);
+        mbar_wait(bar_p_full + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
         issue_pv(j & 1, j > 0);
         umma_commit(bar_pv_done);
+        if (j == T - 1) umma_commit(bar_o_full);
+        if (serial && j + 1 < T) issue_s((j + 1) & 1);  // debugging order: no QK^T / softmax overlap
       }
     }
     __syncwarp();
@@ -259,7 +266,8 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const bool need = mx > m_ref + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
           // O may only be touched once PV_{j-1} has completed.  (S_j was issued BEFORE PV_{j-1}, so s_full says
-          // nothing about it.)  bar_pv_done has completed j-1 or j phases at this point, never more.
+          // nothing about it.)  S_j complete implies PV_{j-2} complete (in-order pipe) and PV_j cannot start before
+          // this thread arrives on p_full, so bar_pv_done has completed exactly j-1 or j phases here: no aliasing.
           mbar_wait(bar_pv_done, (j - 1) & 1);
           tc_fence_after();
           const float m_new = need ? mx : m_ref;
@@ -293,10 +301,10 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p_full);
+      if (lane == 0) mbar_arrive(bar_p_full + 8 * buf);
     }
     // ---- epilogue
-    mbar_wait(bar_pv_done, (T - 1) & 1);
+    mbar_wait(bar_o_full, 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const uint32_t stage_base = smem_ring + q * 32 * 128;  // ring memory is idle now: [chunk][128 rows][128 B]
@@ -356,7 +364,7 @@ extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, v
   if ((rc = make_tmap_3d_u16(&tmK, K, BH, N, D, uint64_t(N) * D, D, 1, 128, 64, 128))) return rc;
   if ((rc = make_tmap_3d_u16(&tmV, V, BH, N, D, uint64_t(N) * D, D, 1, 128, 64, 128))) return rc;
   if ((rc = make_tmap_3d_u16(&tmO, O, BH, N, D, uint64_t(N) * D, D, 1, 32, 64, 128))) return rc;
-  const bool q_resident = (D <= 512) && variant != 2;  // variant 2 forces the streaming-Q path (testing)
+  const bool q_resident = (D <= 512) && !(variant & 2);  // variant 2 forces the streaming-Q path (testing)
   const int q_bytes = q_resident ? int(D / 64) * ffpa::BOX_BYTES : 0;
   int stages = (232448 - 1024 - ffpa::BAR_BYTES - q_bytes) / ffpa::STAGE_BYTES;
   if (stages > ffpa::MAX_STAGES) stages = ffpa::MAX_STAGES;
@@ -367,11 +375,11 @@ extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, v
   if (q_resident) {
     auto kern = ffpa_fwd_tcgen05_kernel<true>;
     B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, ffpa::THREADS, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2);
+    kern<<<grid, ffpa::THREADS, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, (variant & 4) ? 1 : 0);
   } else {
     auto kern = ffpa_fwd_tcgen05_kernel<false>;
     B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, ffpa::THREADS, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2);
+    kern<<<grid, ffpa::THREADS, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, (variant & 4) ? 1 : 0);
   }
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;

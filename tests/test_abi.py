@@ -1,0 +1,50 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/b200k.h declares, and validates
+arguments before touching the device.  No compute is attempted here."""
+import ctypes
+
+import pytest
+
+from b200k import _loader as L
+
+
+def test_header_symbols_are_all_exported_and_bound():
+    declared = L.declared_symbols()
+    assert len(declared) >= 15
+    raw = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), "libb200k.so does not export %s" % name
+    assert sorted(L._SIGS) == declared, "ctypes signature table and include/b200k.h disagree"
+
+
+def test_abi_version_and_workspace():
+    assert L.lib.b200k_abi_version() == 1
+    assert L.lib.b200k_reduce_workspace_bytes() >= 2048 * 4
+
+
+def test_argument_validation_happens_before_cuda():
+    lib = L.lib
+    one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
+    assert lib.b200k_hgemm_f16(None, one, one, 8, 8, 8, 0, 0, None) == L.EARG
+    assert lib.b200k_hgemm_f16(one, one, one, 8, 8, 7, 0, 0, None) == L.ESHAPE
+    assert b"multiples of 8" in lib.b200k_last_error()
+    assert lib.b200k_hgemm_f16(one, one, one, 0, 8, 8, 0, 0, None) == L.ESHAPE
+    assert lib.b200k_fa2_fwd_f16(None, one, one, one, 1, 1, 8, 64, 0.0, 0, 0, None) == L.EARG
+    assert lib.b200k_fa2_fwd_f16(one, one, one, one, 1, 0, 8, 64, 0.0, 0, 0, None) == L.ESHAPE
+    assert lib.b200k_ffpa_fwd_f16(one, one, one, one, 1, 1, 8, 200, 0.0, 0, None) == L.EHEADDIM
+    assert b"headdim not support" in lib.b200k_last_error()
+    assert lib.b200k_elementwise_add(one, one, one, 4, 99, None) in (L.EDTYPE, L.ECUDA, L.EARCH)
+    assert lib.b200k_rope_f32(one, one, 4, 7, 1, None) == L.ESHAPE
+    assert lib.b200k_softmax(one, one, 4, 8, L.F32, 9, None, None) == L.EARG
+    assert lib.b200k_embedding(one, one, one, 4, 4, 4, L.I8, None) == L.EDTYPE
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    one = ctypes.c_void_p(16)
+    rc = L.lib.b200k_hgemm_f16(one, one, one, 128, 128, 128, 0, 0, None)
+    assert rc in (L.ECUDA, L.EARCH) and L.last_error()
+    with pytest.raises(L.B200KError):
+        L.device_info()

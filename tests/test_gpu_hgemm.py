@@ -1,0 +1,105 @@
+"""GPU parity: tcgen05 HGEMM (through the C ABI) vs the CPU oracle, golden fixture, edge shapes, and full-size
+(BASELINE config #2) property checks.  Tolerance: the north star's rtol=1e-2 / atol=1e-3 applies to fp16 outputs of
+O(1) magnitude; GEMM outputs are O(sqrt(K)), so atol is scaled by sqrt(K/64) (what fp16 output rounding alone needs,
+SURVEY.md §7.2-1).  Written in each assert."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(K):
+    return dict(rtol=1e-2, atol=1e-3 * max(1.0, (K / 64.0) ** 0.5))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("tn", [False, True])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (256, 256, 256), (300, 520, 264), (1, 8, 8), (129, 264, 8), (1000, 72, 1000)])
+def test_hgemm_vs_oracle(variant, tn, shape):
+    from b200k import ops
+
+    M, N, K = shape
+    torch.manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, dtype=torch.half, device="cuda")
+    b = torch.randn(K, N, dtype=torch.half, device="cuda")
+    c = torch.full((M, N), float("nan"), dtype=torch.half, device="cuda")
+    bb = b.t().contiguous().t() if tn else b  # [K,N] view over B^T storage, like the reference's as_col_major
+    ops.hgemm(a, bb, c, tn=tn, variant=variant)
+    ref = oracle.hgemm(a, b)
+    assert torch.isfinite(c).all()
+    assert torch.allclose(c.cpu().float(), ref.float(), **_tol(K))
+
+
+def test_hgemm_golden_fixture(golden):
+    from b200k import ops
+
+    g = golden("seeded_hgemm.npz")
+    a = torch.from_numpy(g["a"]).cuda()
+    b = torch.from_numpy(g["b"]).cuda()
+    c = torch.empty(a.size(0), b.size(1), dtype=torch.half, device="cuda")
+    ops.hgemm(a, b, c)
+    want = torch.from_numpy(g["c"]).float()
+    # fp32-accumulating tensor core vs exact accumulate + one rounding: at most 1 fp16 ulp apart
+    assert torch.allclose(c.cpu().float(), want, rtol=2 ** -10, atol=2 ** -10)
+
+
+def test_hgemm_drop_in_names_route_to_kernel():
+    import toy_hgemm
+
+    torch.manual_seed(5)
+    a = torch.randn(256, 128, dtype=torch.half, device="cuda")
+    b = torch.randn(128, 384, dtype=torch.half, device="cuda")
+    ref = oracle.hgemm(a, b).float()
+    b_col_major = b.t().contiguous().t()
+    for name in toy_hgemm.HGEMM_NAMES:
+        c = torch.zeros(256, 384, dtype=torch.half, device="cuda")
+        fn = getattr(toy_hgemm, name)
+        bb = b_col_major if ("_tn" in name) else b
+        if "stages" in name:
+            fn(a, bb, c, 3, True, 2048)
+        else:
+            fn(a, bb, c)
+        assert torch.allclose(c.cpu().float(), ref, **_tol(128)), name
+
+
+@pytest.mark.parametrize("n", [2048, 4096, 8192])
+def test_hgemm_full_size_sampled_entries_and_linearity(n):
+    """BASELINE config #2 sizes: (1) 512 sampled entries against fp64 dot products of the same fp16 inputs,
+    (2) structure: C(A, [B1 | B2]) column blocks equal C(A, B1), C(A, B2) bit for bit (tiles are independent)."""
+    from b200k import ops
+
+    torch.manual_seed(n)
+    a = torch.randn(n, n, dtype=torch.half, device="cuda")
+    b = torch.randn(n, n, dtype=torch.half, device="cuda")
+    c = torch.empty(n, n, dtype=torch.half, device="cuda")
+    ops.hgemm(a, b, c)
+    idx = torch.randint(0, n, (512, 2), device="cuda")
+    want = (a[idx[:, 0]].double() * b[:, idx[:, 1]].t().double()).sum(-1)
+    got = c[idx[:, 0], idx[:, 1]].double()
+    assert torch.allclose(got, want, **_tol(n))
+    half = n // 2
+    c1 = torch.empty(n, half, dtype=torch.half, device="cuda")
+    ops.hgemm(a, b[:, :half].contiguous(), c1)
+    assert torch.equal(c1, c[:, :half])
+
+
+def test_hgemm_16384_smoke_and_stream():
+    """Largest sweep size (3 x 512 MiB operands) on a side stream: sampled entries only."""
+    from b200k import ops
+
+    n = 16384
+    torch.manual_seed(2)
+    a = torch.randn(n, n, dtype=torch.half, device="cuda")
+    b = torch.randn(n, n, dtype=torch.half, device="cuda")
+    c = torch.empty(n, n, dtype=torch.half, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ops.hgemm(a, b, c)
+    s.synchronize()
+    idx = torch.randint(0, n, (128, 2), device="cuda")
+    want = (a[idx[:, 0]].double() * b[:, idx[:, 1]].t().double()).sum(-1)
+    assert torch.allclose(c[idx[:, 0], idx[:, 1]].double(), want, **_tol(n))

@@ -83,7 +83,7 @@ def test_row_kernels_oracle(golden):
     assert torch.allclose(r.pow(2).mean(-1), torch.ones(x.size(0)), atol=1e-3)
     # the reference's f16 kernels put eps inside K: rsqrt(sum/(K+eps)); difference is O(eps/K)
     r2 = oracle.rms_norm(x, 1.0, eps_inside_k=True)
-    assert (r - r2).abs().max() < 1e-5 and not torch.equal(r, r2)
+    assert (r - r2).abs().max() < 1e-4 and not torch.equal(r, r2)
     assert abs(oracle.reduce_sum(x) - float(g["sum"])) < 1e-9
 
 
