@@ -51,55 +51,59 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / throttle reasons through NVML every ~2 ms while the timed region runs (the timed
+    region of a GEMM step is tens of milliseconds: `nvidia-smi -lms` is too coarse for it)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.err = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((time.perf_counter(), sm, reasons, pw))
+                time.sleep(0.002)
+        except Exception as e:  # noqa
+            self.err = repr(e)[:200]
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+        time.sleep(0.02)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def mark(self):
+        return time.perf_counter()
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], None, [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-                pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        rows = [r for r in self.samples if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)] or self.samples
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= int(r[2])
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        reasons = sorted(n for b, n in names.items() if bits & b)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": getattr(self, "max_mhz", None),
+                "power_w_max": max(r[3] for r in rows), "samples": len(rows), "reasons": reasons,
+                "how": "NVML polled every ~2 ms during the timed steps"}
 
 
 def cuda_time(fn, steps, warmup, barrier=None):
@@ -276,11 +280,16 @@ def main():
     def step():
         ops.hgemm(a, b, c)
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
     if rank == 0:
         sampler.start()
-    ms = cuda_time(step, args.steps, args.warmup, barrier)
-    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    t_mark0 = sampler.mark()
+    ms = cuda_time(step, args.steps, 0, barrier)
+    t_mark1 = sampler.mark()
+    clocks = sampler.stop(t_mark0, t_mark1) if rank == 0 else None
     launches += args.steps
     ms_max = max_over_ranks(ms, dist_on)
     value = flops * world / (ms_max * 1e-3) * 1e-12

@@ -60,7 +60,7 @@ template <class Cfg>
 __global__ void __launch_bounds__(256, 1)
 hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n,
-                     int group_m) {
+                     int group_m, uint64_t policy_a, uint64_t policy_b) {
   constexpr int CG = Cfg::CG, BN = Cfg::BN, STAGES = Cfg::STAGES;
   constexpr bool B_MN = Cfg::B_MN;
   extern __shared__ uint8_t smem_raw[];
@@ -129,23 +129,23 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // all bytes of both CTAs are accounted on the leader's barrier
             if (leader) mbar_arrive_expect_tx(fb_local, 2 * Cfg::STAGE_BYTES);
             const uint32_t fb = mapa(fb_local, 0);
-            tma_load_2d_2sm(sa, &tmA, fb, k0, m0, kPolicyEvictNormal);
+            tma_load_2d_2sm(sa, &tmA, fb, k0, m0, policy_a);
             if constexpr (B_MN) {
 #pragma unroll
               for (int j = 0; j < Cfg::BN_CTA / 64; ++j)
-                tma_load_2d_2sm(sb + j * 8192, &tmB, fb, n0 + j * 64, k0, kPolicyEvictNormal);
+                tma_load_2d_2sm(sb + j * 8192, &tmB, fb, n0 + j * 64, k0, policy_b);
             } else {
-              tma_load_2d_2sm(sb, &tmB, fb, k0, n0, kPolicyEvictNormal);
+              tma_load_2d_2sm(sb, &tmB, fb, k0, n0, policy_b);
             }
           } else {
             mbar_arrive_expect_tx(fb_local, Cfg::STAGE_BYTES);
-            tma_load_2d(sa, &tmA, fb_local, k0, m0, kPolicyEvictNormal);
+            tma_load_2d(sa, &tmA, fb_local, k0, m0, policy_a);
             if constexpr (B_MN) {
 #pragma unroll
               for (int j = 0; j < Cfg::BN_CTA / 64; ++j)
-                tma_load_2d(sb + j * 8192, &tmB, fb_local, n0 + j * 64, k0, kPolicyEvictNormal);
+                tma_load_2d(sb + j * 8192, &tmB, fb_local, n0 + j * 64, k0, policy_b);
             } else {
-              tma_load_2d(sb, &tmB, fb_local, k0, n0, kPolicyEvictNormal);
+              tma_load_2d(sb, &tmB, fb_local, k0, n0, policy_b);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -253,7 +253,7 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 template <class Cfg>
 static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
-                        const DeviceInfo& di) {
+                        const DeviceInfo& di, int tune) {
   CUtensorMap tmA, tmB, tmC;
   int rc;
   if ((rc = make_tmap_2d_u16(&tmA, A, M, K, K, Cfg::BM_CTA, Cfg::BK, true))) return rc;
@@ -267,7 +267,16 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   const int64_t num_tiles = int64_t(tiles_m) * tiles_n;
   const int max_clusters = di.sm_count / Cfg::CG;
   const int clusters = int(num_tiles < max_clusters ? num_tiles : max_clusters);
-  const int group_m = 8;
+  // tune (experiments): bits [8,16) override GROUP_M, bits [16,20) select the L2 eviction hints of the TMA loads.
+  int group_m = 8;
+  if ((tune >> 8) & 0xff) group_m = (tune >> 8) & 0xff;
+  uint64_t policy_a = kPolicyEvictNormal, policy_b = kPolicyEvictNormal;
+  switch ((tune >> 16) & 0xf) {
+    case 1: policy_a = kPolicyEvictLast; policy_b = kPolicyEvictFirst; break;  // A panels are re-used by the next wave
+    case 2: policy_a = kPolicyEvictLast; policy_b = kPolicyEvictNormal; break;
+    case 3: policy_a = kPolicyEvictLast; policy_b = kPolicyEvictLast; break;
+    default: break;
+  }
 
   auto kern = hgemm_tcgen05_kernel<Cfg>;
   static bool attr_set[64] = {};
@@ -287,7 +296,7 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, int(M), int(N), int(K), tiles_m, tiles_n, group_m));
+  B200K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, int(M), int(N), int(K), tiles_m, tiles_n, group_m, policy_a, policy_b));
   return B200K_OK;
 }
 
@@ -307,22 +316,26 @@ extern "C" int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M,
   int rc = get_device_info(&di);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int tune = variant & ~0xff;
+  variant &= 0xff;
   if (variant == B200K_HGEMM_AUTO) {
-    // 256x256 pair tiles when they fill the machine; the narrower pair tile for small problems.
+    // 256x256 pair tiles (best smem/L2 traffic per flop) unless they would leave most of the machine idle; then the
+    // 1-CTA 128x256 tile doubles the number of work units.  (The 256x128 pair tile is L2-bandwidth bound: measured
+    // 0.59x of the 256x256 tile at 2048^3, profiles/r01_hgemm_bringup_check.jsonl.)
     const int64_t t256 = ((M + 255) / 256) * ((N + 255) / 256);
-    variant = (t256 >= (di.sm_count / 2)) ? B200K_HGEMM_2CTA_256x256 : B200K_HGEMM_2CTA_256x128;
+    variant = (t256 * 4 >= di.sm_count) ? B200K_HGEMM_2CTA_256x256 : B200K_HGEMM_1CTA_128x256;
   }
   const bool nn = (b_is_nk == 0);
   switch (variant) {
     case B200K_HGEMM_1CTA_128x256:
-      return nn ? launch_hgemm<GemmCfg<1, 256, true, 4>>(A, B, C, M, N, K, s, di)
-                : launch_hgemm<GemmCfg<1, 256, false, 4>>(A, B, C, M, N, K, s, di);
+      return nn ? launch_hgemm<GemmCfg<1, 256, true, 4>>(A, B, C, M, N, K, s, di, tune)
+                : launch_hgemm<GemmCfg<1, 256, false, 4>>(A, B, C, M, N, K, s, di, tune);
     case B200K_HGEMM_2CTA_256x256:
-      return nn ? launch_hgemm<GemmCfg<2, 256, true, 6>>(A, B, C, M, N, K, s, di)
-                : launch_hgemm<GemmCfg<2, 256, false, 6>>(A, B, C, M, N, K, s, di);
+      return nn ? launch_hgemm<GemmCfg<2, 256, true, 6>>(A, B, C, M, N, K, s, di, tune)
+                : launch_hgemm<GemmCfg<2, 256, false, 6>>(A, B, C, M, N, K, s, di, tune);
     case B200K_HGEMM_2CTA_256x128:
-      return nn ? launch_hgemm<GemmCfg<2, 128, true, 8>>(A, B, C, M, N, K, s, di)
-                : launch_hgemm<GemmCfg<2, 128, false, 8>>(A, B, C, M, N, K, s, di);
+      return nn ? launch_hgemm<GemmCfg<2, 128, true, 8>>(A, B, C, M, N, K, s, di, tune)
+                : launch_hgemm<GemmCfg<2, 128, false, 8>>(A, B, C, M, N, K, s, di, tune);
     default:
       return set_error(B200K_EARG, "b200k_hgemm_f16: unknown variant %d", variant);
   }
