@@ -65,6 +65,7 @@ _SIGS = {
     "b200k_max_i32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "b200k_histogram_i32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "b200k_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "b200k_debug_set_trace": (c_int, [c_void_p]),
 }
 
 

@@ -1,15 +1,19 @@
 // FlashAttention-2 forward for B200 (sm_100a):  O = softmax(Q K^T * scale) V,  [B,H,N,D] fp16, non-causal.
 //
-// One CTA owns 256 query rows of one (batch, head): two 128-row Q tiles that ping-pong on the tensor core.
-//   warp 0        TMA producer: Q tiles once, then a ring of K and V tiles (128 keys each), 128B/64B-swizzled smem
-//   warp 1        MMA issuer (one thread):  S_i = Q_i K_j^T   (tcgen05.mma SS, fp32 accumulate, 128x128 into TMEM)
+// One CTA owns 256 query rows of one (batch, head): two 128-row Q tiles that share every K/V tile.
+//   warp 0        TMA producer: Q tiles once, then rings of K and V tiles (BC keys each), 128B/64B-swizzled smem
+//   warp 1        MMA issuer (one thread):  S_i = Q_i K_j^T   (tcgen05.mma SS, fp32 accumulate, 128 x BC into TMEM)
 //                                            O_i += P_ij V_j   (tcgen05.mma TS: P read from TMEM, V MN-major smem)
-//   warp 2        TMEM allocator (512 columns: S0 S1 | O0 O1)
+//   warp 2        TMEM allocator
 //   warps 4..7    softmax warpgroup for Q tile 0, one thread per query row: tcgen05.ld the S row, online softmax
-//   warps 8..11   softmax warpgroup for Q tile 1       (row max / exp2 / row sum in fp32 registers), P written back
-//                 as fp16 over the S columns with tcgen05.st; O is rescaled in TMEM only when the row max grew by
-//                 more than 2^8 (lazy rescaling); the same threads normalise and store O at the end (TMA store).
-// While one warpgroup does softmax on its tile the tensor core works for the other tile.
+//   warps 8..11   softmax warpgroup for Q tile 1       (row max / exp2 / row sum in fp32 registers), P written as
+//                 fp16 into its OWN TMEM columns with tcgen05.st; O is rescaled in TMEM only when the row max grew
+//                 by more than 2^8 (lazy rescaling); the same threads normalise and store O at the end (TMA store).
+// TMEM columns:  S0 S1 (2 x BC fp32) | P0 P1 (2 x BC/2, packed fp16) | O0 O1 (2 x D fp32)   <= 512.
+// Because P does not alias S, the scores of KV tile j+1 are produced while the softmax warps still work on tile j:
+// the S columns are handed back right after the row has been read into registers (s_free), so a softmax
+// warpgroup never waits for the tensor core in steady state; PV of tile j overlaps softmax of tile j+1.
+// BC = 128 keys for D <= 64; BC = 64 for D = 96 / 128 so that the layout fits the 512 columns.
 //
 // Replaces kernels/flash-attn/mma/basic/flash_attn_mma_share_qkv.cu:L45-709 (kernel) / L711-886 (launcher) and the
 // other flash_attn_mma_stages_* variants (same math, different Ampere smem strategies).  Numerics follow the
@@ -22,26 +26,31 @@
 
 namespace b200k {
 
-template <int D_, int STAGES_, bool V_DN_ = false>
+template <int D_, int BC_, int STAGES_, bool V_DN_ = false>
 struct Fa2Cfg {
   static constexpr int D = D_;
-  static constexpr bool V_DN = V_DN_;  // V passed transposed as [B,H,D,N] (the reference's *_swizzle_qkv entry points)
+  static constexpr int BC = BC_;                       // keys per KV tile
   static constexpr int STAGES = STAGES_;
+  static constexpr bool V_DN = V_DN_;  // V passed transposed as [B,H,D,N] (the reference's *_swizzle_qkv entry points)
   static constexpr int CW = (D % 64 == 0) ? 64 : 32;  // width of one smem chunk along D (elements)
   static constexpr int NCH = D / CW;
   static constexpr int ROWB = CW * 2;                  // bytes per smem row = swizzle span (128 or 64)
   static constexpr uint32_t SWZ_MODE = (ROWB == 128) ? 2u : 4u;
   static constexpr int BR = 128;                       // query rows per tile (= TMEM lanes)
-  static constexpr int BC = 128;                       // keys per KV tile
-  static constexpr int CHUNK_BYTES = 128 * ROWB;       // one TMA box: 128 rows x CW elements
-  static constexpr int TILE_BYTES = NCH * CHUNK_BYTES; // a 128 x D tile
+  static constexpr int Q_CHUNK_BYTES = 128 * ROWB;     // one TMA box of Q: 128 rows x CW elements
+  static constexpr int Q_TILE_BYTES = NCH * Q_CHUNK_BYTES;
+  static constexpr int KV_CHUNK_BYTES = BC * ROWB;     // one TMA box of K or V: BC rows x CW elements
+  static constexpr int KV_TILE_BYTES = NCH * KV_CHUNK_BYTES;  // = BC * D * 2 (also for the transposed-V layout)
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int SMEM_BYTES = 1024 + BAR_BYTES + 2 * TILE_BYTES + 2 * STAGES * TILE_BYTES;
-  static constexpr int S_COL0 = 0, S_COL1 = 128;
-  static constexpr int O_COL0 = 256, O_COL1 = 256 + D;
+  static constexpr int SMEM_BYTES = 1024 + BAR_BYTES + 2 * Q_TILE_BYTES + 2 * STAGES * KV_TILE_BYTES;
+  static constexpr int S_COL0 = 0, S_COL1 = BC;
+  static constexpr int P_COL0 = 2 * BC, P_COL1 = 2 * BC + BC / 2;
+  static constexpr int O_COL0 = 3 * BC, O_COL1 = 3 * BC + D;
   static constexpr int TMEM_COLS = 512;
   static constexpr int THREADS = 384;
   static_assert(D % 32 == 0 && D >= 32 && D <= 128, "head dim");
+  static_assert(BC == 64 || BC == 128, "keys per tile");
+  static_assert(3 * BC + 2 * D <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 232448, "smem");
 };
 
@@ -49,37 +58,51 @@ struct Fa2Cfg {
 // have ample range), so the O accumulator is touched only on the first few KV tiles of a row.
 constexpr float kRescaleThreshold = 8.0f;
 
-template <class Cfg>
+// Optional cycle trace of CTA (0,0) for pipeline analysis (tools/gpu_trace_fa2.py): trace[role][j][event] = clock64(),
+// role 0 = MMA thread, 1 = softmax warp 4 (Q tile 0), 2 = softmax warp 8 (Q tile 1); first kTraceIters KV tiles.
+constexpr int kTraceIters = 32, kTraceEvents = 8;
+static unsigned long long* g_fa2_trace = nullptr;  // set through b200k_debug_set_trace()
+
+template <class Cfg, bool TRACE>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int N,
-                       float scale_log2) {
-  constexpr int D = Cfg::D, STAGES = Cfg::STAGES, NCH = Cfg::NCH, CW = Cfg::CW, ROWB = Cfg::ROWB;
+                       float scale_log2, unsigned long long* trace, int pingpong) {
+  auto tr = [&](int role, int j, int ev) {
+    if constexpr (TRACE) {
+      if (blockIdx.x == 0 && blockIdx.y == 0 && j < kTraceIters)
+        trace[(role * kTraceIters + j) * kTraceEvents + ev] = clock64();
+    }
+  };
+  constexpr int D = Cfg::D, BC = Cfg::BC, STAGES = Cfg::STAGES, NCH = Cfg::NCH, CW = Cfg::CW, ROWB = Cfg::ROWB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
 
-  // barriers
+  // barriers (8 bytes each)
   const uint32_t bar_q_full = base;                       // 2
   const uint32_t bar_k_full = base + 16;                  // STAGES
   const uint32_t bar_k_empty = bar_k_full + 8 * STAGES;   // STAGES
   const uint32_t bar_v_full = bar_k_empty + 8 * STAGES;   // STAGES
   const uint32_t bar_v_empty = bar_v_full + 8 * STAGES;   // STAGES
-  const uint32_t bar_s_full = bar_v_empty + 8 * STAGES;   // 2   S_i ready            (MMA -> softmax i)
-  const uint32_t bar_p_full = bar_s_full + 16;            // 2   P_i written, O_i ok  (softmax i -> MMA)
-  const uint32_t bar_o_full = bar_p_full + 16;            // 2   last PV_i done       (MMA -> softmax i)
+  const uint32_t bar_s_full = bar_v_empty + 8 * STAGES;   // 2   S_i(j) ready                 (MMA -> softmax i)
+  const uint32_t bar_s_free = bar_s_full + 16;            // 2   S_i(j) is in registers       (softmax i -> MMA)
+  const uint32_t bar_p_full = bar_s_free + 16;            // 2   P_i(j) written, O_i rescaled (softmax i -> MMA)
+  const uint32_t bar_p_free = bar_p_full + 16;            // 2   PV_i(j) done: P_i free, O_i stable (MMA -> softmax i)
+  const uint32_t bar_o_full = bar_p_free + 16;            // 2   last PV_i done               (MMA -> softmax i)
   const uint32_t tmem_slot = bar_o_full + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
-  const uint32_t smem_q = base + Cfg::BAR_BYTES;                  // 2 tiles
-  const uint32_t smem_k = smem_q + 2 * Cfg::TILE_BYTES;           // STAGES tiles
-  const uint32_t smem_v = smem_k + STAGES * Cfg::TILE_BYTES;      // STAGES tiles
+  const uint32_t smem_q = base + Cfg::BAR_BYTES;                      // 2 Q tiles
+  const uint32_t smem_k = smem_q + 2 * Cfg::Q_TILE_BYTES;             // STAGES K tiles
+  const uint32_t smem_v = smem_k + STAGES * Cfg::KV_TILE_BYTES;       // STAGES V tiles
 
-  const uint32_t warp = threadIdx.x >> 5;
+  // warp index via shuffle: the compiler then knows it is warp-uniform and keeps role code on the uniform datapath
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int q0 = blockIdx.x * 256;
-  const int T = (N + Cfg::BC - 1) / Cfg::BC;  // KV tiles
+  const int T = (N + BC - 1) / BC;  // KV tiles
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -89,7 +112,9 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_q_full + 8 * i, 1);
       mbar_init(bar_s_full + 8 * i, 1);
+      mbar_init(bar_s_free + 8 * i, 4);
       mbar_init(bar_p_full + 8 * i, 4);
+      mbar_init(bar_p_free + 8 * i, 1);
       mbar_init(bar_o_full + 8 * i, 1);
     }
     for (int s = 0; s < STAGES; ++s) {
@@ -109,146 +134,200 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp < 4) {
   if (warp == 0) {
     // ---------------------------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      auto load_tile = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int row0, uint64_t policy) {
-        mbar_arrive_expect_tx(bar, Cfg::TILE_BYTES);
+    // (whole warp convergent, one elected lane issues: keeps addresses / coordinates on the uniform datapath)
+    {
+      auto load_q = [&](int i) {
+        const uint32_t bar = bar_q_full + 8 * i;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar, Cfg::Q_TILE_BYTES);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) tma_load_3d(dst + c * Cfg::CHUNK_BYTES, tm, bar, c * CW, row0, bh, policy);
-      };
-      load_tile(&tmQ, smem_q, bar_q_full, q0, kPolicyEvictFirst);
-      for (int j = 0; j < T; ++j) {
-        const int s = j % STAGES;
-        const uint32_t ph = (j / STAGES) & 1;
-        mbar_wait(bar_k_empty + 8 * s, ph ^ 1);
-        load_tile(&tmK, smem_k + s * Cfg::TILE_BYTES, bar_k_full + 8 * s, j * Cfg::BC, kPolicyEvictLast);
-        if (j == 0) load_tile(&tmQ, smem_q + Cfg::TILE_BYTES, bar_q_full + 8, q0 + 128, kPolicyEvictFirst);
-        mbar_wait(bar_v_empty + 8 * s, ph ^ 1);
-        if constexpr (Cfg::V_DN) {
-          // V^T tile: D rows x 128 keys, as two [D rows x 64 keys] 128B-swizzled boxes (keys contiguous = K-major B)
-          const uint32_t dst = smem_v + s * Cfg::TILE_BYTES;
-          mbar_arrive_expect_tx(bar_v_full + 8 * s, Cfg::TILE_BYTES);
-          tma_load_3d(dst, &tmV, bar_v_full + 8 * s, j * Cfg::BC, 0, bh, kPolicyEvictLast);
-          tma_load_3d(dst + D * 128, &tmV, bar_v_full + 8 * s, j * Cfg::BC + 64, 0, bh, kPolicyEvictLast);
-        } else {
-          load_tile(&tmV, smem_v + s * Cfg::TILE_BYTES, bar_v_full + 8 * s, j * Cfg::BC, kPolicyEvictLast);
+          for (int c = 0; c < NCH; ++c)
+            tma_load_3d(smem_q + i * Cfg::Q_TILE_BYTES + c * Cfg::Q_CHUNK_BYTES, &tmQ, bar, c * CW, q0 + i * 128, bh,
+                        kPolicyEvictFirst);
         }
+        __syncwarp();
+      };
+      auto load_k = [&](int j) {
+        const int s = j % STAGES;
+        mbar_wait(bar_k_empty + 8 * s, ((j / STAGES) & 1) ^ 1);
+        const uint32_t bar = bar_k_full + 8 * s;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar, Cfg::KV_TILE_BYTES);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+            tma_load_3d(smem_k + s * Cfg::KV_TILE_BYTES + c * Cfg::KV_CHUNK_BYTES, &tmK, bar, c * CW, j * BC, bh,
+                        kPolicyEvictLast);
+        }
+        __syncwarp();
+      };
+      auto load_v = [&](int j) {
+        const int s = j % STAGES;
+        mbar_wait(bar_v_empty + 8 * s, ((j / STAGES) & 1) ^ 1);
+        const uint32_t bar = bar_v_full + 8 * s;
+        const uint32_t dst = smem_v + s * Cfg::KV_TILE_BYTES;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar, Cfg::KV_TILE_BYTES);
+          if constexpr (Cfg::V_DN) {
+            // V^T tile: D rows x BC keys, as [D rows x 64 keys] 128B-swizzled boxes (keys contiguous = K-major B operand)
+#pragma unroll
+            for (int c = 0; c < BC / 64; ++c)
+              tma_load_3d(dst + c * (D * 128), &tmV, bar, j * BC + c * 64, 0, bh, kPolicyEvictLast);
+          } else {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+              tma_load_3d(dst + c * Cfg::KV_CHUNK_BYTES, &tmV, bar, c * CW, j * BC, bh, kPolicyEvictLast);
+          }
+        }
+        __syncwarp();
+      };
+      load_q(0);
+      load_k(0);
+      load_q(1);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) load_k(j + 1);
+        load_v(j);
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_f16(128, Cfg::BC, true, false, false);  // Q, K both K-major (D contiguous)
+    // The whole warp runs this loop convergently (waits, address arithmetic: warp-uniform, uniform datapath); the
+    // tcgen05.mma / commit instructions themselves are issued by one elected lane.
+    {
+      constexpr uint32_t idesc_s = make_idesc_f16(128, BC, true, false, false);  // Q, K both K-major (D contiguous)
       // P from TMEM; V is MN-major ([keys, D], D contiguous) or, for V^T input, K-major ([D, keys], keys contiguous)
       constexpr uint32_t idesc_o = make_idesc_f16(128, D, true, false, !Cfg::V_DN);
       constexpr uint64_t qk_hi = make_smem_desc_hi(16, 8 * ROWB, Cfg::SWZ_MODE);
       constexpr uint64_t v_hi = Cfg::V_DN ? make_smem_desc_hi(16, 1024, kSwizzle128B)
-                                          : make_smem_desc_hi(Cfg::CHUNK_BYTES, 8 * ROWB, Cfg::SWZ_MODE);
+                                          : make_smem_desc_hi(Cfg::KV_CHUNK_BYTES, 8 * ROWB, Cfg::SWZ_MODE);
       constexpr int KSTEPS_PER_CHUNK = CW / 16;
 
-      auto issue_s = [&](int i, int stage) {
-        const uint32_t q_addr = smem_q + i * Cfg::TILE_BYTES;
-        const uint32_t k_addr = smem_k + stage * Cfg::TILE_BYTES;
+      // S_i = Q_i K^T, then commit to `bar_a` (and optionally `bar_b`)
+      auto issue_s = [&](int i, int stage, uint32_t bar_a, uint32_t bar_b) {
+        const uint32_t q_addr = smem_q + i * Cfg::Q_TILE_BYTES;
+        const uint32_t k_addr = smem_k + stage * Cfg::KV_TILE_BYTES;
         const uint32_t d_tmem = tmem_base + (i ? Cfg::S_COL1 : Cfg::S_COL0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k / KSTEPS_PER_CHUNK) * Cfg::CHUNK_BYTES + (k % KSTEPS_PER_CHUNK) * 32;
-          umma_ss<1>(d_tmem, smem_desc(qk_hi, q_addr + off), smem_desc(qk_hi, k_addr + off), idesc_s, k != 0);
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t q_off = (k / KSTEPS_PER_CHUNK) * Cfg::Q_CHUNK_BYTES + (k % KSTEPS_PER_CHUNK) * 32;
+            const uint32_t k_off = (k / KSTEPS_PER_CHUNK) * Cfg::KV_CHUNK_BYTES + (k % KSTEPS_PER_CHUNK) * 32;
+            umma_ss<1>(d_tmem, smem_desc(qk_hi, q_addr + q_off), smem_desc(qk_hi, k_addr + k_off), idesc_s, k != 0);
+          }
+          umma_commit(bar_a);
+          if (bar_b) umma_commit(bar_b);
         }
+        __syncwarp();
       };
-      auto issue_pv = [&](int i, int stage, bool accumulate) {
-        const uint32_t v_addr = smem_v + stage * Cfg::TILE_BYTES;
+      auto issue_pv = [&](int i, int stage, bool accumulate, uint32_t bar_a, uint32_t bar_b, uint32_t bar_c) {
+        const uint32_t v_addr = smem_v + stage * Cfg::KV_TILE_BYTES;
         const uint32_t d_tmem = tmem_base + (i ? Cfg::O_COL1 : Cfg::O_COL0);
-        const uint32_t p_tmem = tmem_base + (i ? Cfg::S_COL1 : Cfg::S_COL0);
+        const uint32_t p_tmem = tmem_base + (i ? Cfg::P_COL1 : Cfg::P_COL0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < Cfg::BC / 16; ++k) {
-          // 16 keys = 8 packed fp16x2 columns of P; 16 rows of V = 16 * ROWB bytes (V^T: 32 bytes inside a 64-key box)
-          const uint32_t v_off = Cfg::V_DN ? uint32_t((k / 4) * (D * 128) + (k % 4) * 32) : uint32_t(k * 16 * ROWB);
-          umma_ts<1>(d_tmem, p_tmem + k * 8, smem_desc(v_hi, v_addr + v_off), idesc_o,
-                     (accumulate || k != 0) ? 1u : 0u);
+          for (int k = 0; k < BC / 16; ++k) {
+            // 16 keys = 8 packed fp16x2 columns of P; 16 rows of V = 16 * ROWB bytes (V^T: 32 bytes inside a 64-key box)
+            const uint32_t v_off = Cfg::V_DN ? uint32_t((k / 4) * (D * 128) + (k % 4) * 32) : uint32_t(k * 16 * ROWB);
+            umma_ts<1>(d_tmem, p_tmem + k * 8, smem_desc(v_hi, v_addr + v_off), idesc_o,
+                       (accumulate || k != 0) ? 1u : 0u);
+          }
+          umma_commit(bar_a);
+          if (bar_b) umma_commit(bar_b);
+          if (bar_c) umma_commit(bar_c);
         }
+        __syncwarp();
       };
 
       mbar_wait(bar_q_full, 0);
       mbar_wait(bar_k_full, 0);
       tc_fence_after();
-      issue_s(0, 0);
-      umma_commit(bar_s_full);
+      issue_s(0, 0, bar_s_full, 0);
       mbar_wait(bar_q_full + 8, 0);
       tc_fence_after();
-      issue_s(1, 0);
-      umma_commit(bar_s_full + 8);
-      umma_commit(bar_k_empty);
+      issue_s(1, 0, bar_s_full + 8, bar_k_empty);
       for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) {
+          // scores of the next KV tile: only needs the S columns back (the softmax warps hold tile j in registers)
+          const int s1 = (j + 1) % STAGES;
+          mbar_wait(bar_k_full + 8 * s1, ((j + 1) / STAGES) & 1);
+          if (lane == 0) tr(0, j, 0);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            mbar_wait(bar_s_free + 8 * i, j & 1);
+            if (lane == 0) tr(0, j, 1 + 2 * i);
+            tc_fence_after();
+            issue_s(i, s1, bar_s_full + 8 * i, i == 1 ? bar_k_empty + 8 * s1 : 0u);
+            if (lane == 0) tr(0, j, 2 + 2 * i);
+          }
+        }
         const int s = j % STAGES;
-        const uint32_t ph = (j / STAGES) & 1;
-        const int s1 = (j + 1) % STAGES;
-        const uint32_t ph1 = ((j + 1) / STAGES) & 1;
-        mbar_wait(bar_v_full + 8 * s, ph);
+        mbar_wait(bar_v_full + 8 * s, (j / STAGES) & 1);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           mbar_wait(bar_p_full + 8 * i, j & 1);
+          if (lane == 0) tr(0, j, 5 + i);
           tc_fence_after();
-          issue_pv(i, s, j > 0);
-          if (j == T - 1) umma_commit(bar_o_full + 8 * i);
-          if (i == 1) umma_commit(bar_v_empty + 8 * s);
-          if (j + 1 < T) {
-            if (i == 0) {
-              mbar_wait(bar_k_full + 8 * s1, ph1);
-              tc_fence_after();
-            }
-            issue_s(i, s1);
-            umma_commit(bar_s_full + 8 * i);
-            if (i == 1) umma_commit(bar_k_empty + 8 * s1);
-          }
+          issue_pv(i, s, j > 0, bar_p_free + 8 * i, (j == T - 1) ? bar_o_full + 8 * i : 0u,
+                   i == 1 ? bar_v_empty + 8 * s : 0u);
         }
+        if (lane == 0) tr(0, j, 7);
       }
     }
-    __syncwarp();
-  }
-  } else {
+  } else if (warp >= 4) {
     // ---------------------------------------------------------------------------------- softmax + epilogue
     const int i = (warp >= 8) ? 1 : 0;                  // which Q tile
     const uint32_t q = warp & 3;                         // TMEM lane quadrant
     const uint32_t lane_base = (q * 32) << 16;
     const uint32_t s_tmem = tmem_base + lane_base + (i ? Cfg::S_COL1 : Cfg::S_COL0);
+    const uint32_t p_tmem = tmem_base + lane_base + (i ? Cfg::P_COL1 : Cfg::P_COL0);
     const uint32_t o_tmem = tmem_base + lane_base + (i ? Cfg::O_COL1 : Cfg::O_COL0);
     float m_ref = -INFINITY;  // reference max, in log2-scaled units
     float l = 0.f;
+    // Optional turn-taking of the exp2 phase between the two warpgroups (named barriers 1 and 2, 256 threads): while
+    // one warpgroup owns the MUFU pipe the other does its load / max / store / handshake work, instead of both
+    // drifting into lock-step and leaving the MUFU idle during those phases.
+    if (pingpong && i == 1) named_bar_arrive(1, 256);
     for (int j = 0; j < T; ++j) {
       mbar_wait(bar_s_full + 8 * i, j & 1);
+      const bool tw = TRACE && lane == 0 && q == 0;  // one thread per warpgroup writes the trace
+      if (tw) tr(1 + i, j, 0);
       tc_fence_after();
-      uint32_t sr[128];
-      tmem_ld_32x32b_x32(s_tmem, sr);
-      tmem_ld_32x32b_x32(s_tmem + 32, sr + 32);
-      tmem_ld_32x32b_x32(s_tmem + 64, sr + 64);
-      tmem_ld_32x32b_x32(s_tmem + 96, sr + 96);
-      tmem_wait_ld();
-      float* s = reinterpret_cast<float*>(sr);
-      if (j == T - 1 && (N % Cfg::BC) != 0) {
-        const int valid = N - j * Cfg::BC;
+      uint32_t sr[BC];
 #pragma unroll
-        for (int c = 0; c < 128; ++c)
+      for (int c = 0; c < BC / 32; ++c) tmem_ld_32x32b_x32(s_tmem + c * 32, sr + c * 32);
+      tmem_wait_ld();
+      if (tw) tr(1 + i, j, 1);
+      // the scores are in registers: give the S columns back so that S(j+1) is computed under this softmax
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_free + 8 * i);
+      float* s = reinterpret_cast<float*>(sr);
+      if (j == T - 1 && (N % BC) != 0) {
+        const int valid = N - j * BC;
+#pragma unroll
+        for (int c = 0; c < BC; ++c)
           if (c >= valid) s[c] = -INFINITY;
       }
       float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-      for (int c = 4; c < 128; c += 4) {
+      for (int c = 4; c < BC; c += 4) {
         mx0 = fmaxf(mx0, s[c]);
         mx1 = fmaxf(mx1, s[c + 1]);
         mx2 = fmaxf(mx2, s[c + 2]);
         mx3 = fmaxf(mx3, s[c + 3]);
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      bool pv_done = (j == 0);  // has PV_i(j-1) been observed complete (O_i stable, P_i columns free)?
       if (j == 0) {
         m_ref = mx;
       } else {
         const bool need = mx > m_ref + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
           // warp-uniform: rescale this warp's 32 rows of O (rows that did not move use alpha = 1)
+          mbar_wait(bar_p_free + 8 * i, (j - 1) & 1);
+          tc_fence_after();
+          pv_done = true;
           const float m_new = need ? mx : m_ref;
           const float alpha = fast_exp2(m_ref - m_new);
           m_ref = m_new;
@@ -265,30 +344,52 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tmem_wait_st();
         }
       }
+      if (pingpong) named_bar_sync(1 + i, 256);
+      if (tw) tr(1 + i, j, 2);
       // P = exp2(s * scale_log2 - m_ref), row sum in fp32, P packed to fp16 pairs in place
-      float l0 = 0.f, l1 = 0.f;
+      // processed in blocks of 16: all FFMAs, then all MUFU.EX2, then sums / packs, so that 16 independent
+      // exponentials are in flight per thread (the MUFU pipe is the bound of this loop)
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       const float neg_m = -m_ref;
 #pragma unroll
-      for (int c = 0; c < 128; c += 2) {
-        const float p0 = fast_exp2(fmaf(s[c], scale_log2, neg_m));
-        const float p1 = fast_exp2(fmaf(s[c + 1], scale_log2, neg_m));
-        l0 += p0;
-        l1 += p1;
-        sr[c >> 1] = pack_half2(p0, p1);
+      for (int c0 = 0; c0 < BC; c0 += 16) {
+        float x[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) x[e] = fmaf(s[c0 + e], scale_log2, neg_m);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) x[e] = fast_exp2(x[e]);
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          l0 += x[e];
+          l1 += x[e + 1];
+          l2 += x[e + 2];
+          l3 += x[e + 3];
+          sr[(c0 + e) >> 1] = pack_half2(x[e], x[e + 1]);
+          sr[((c0 + e) >> 1) + 1] = pack_half2(x[e + 2], x[e + 3]);
+        }
       }
-      l += l0 + l1;
-      tmem_st_32x32b_x32(s_tmem, sr);
-      tmem_st_32x32b_x32(s_tmem + 32, sr + 32);
+      l += (l0 + l1) + (l2 + l3);
+      if (pingpong) named_bar_arrive(2 - i, 256);
+      if (tw) tr(1 + i, j, 3);
+      if (!pv_done) {  // P_i(j-1) must have been consumed before it is overwritten (normally long since true)
+        mbar_wait(bar_p_free + 8 * i, (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (tw) tr(1 + i, j, 4);
+#pragma unroll
+      for (int c = 0; c < BC / 64; ++c) tmem_st_32x32b_x32(p_tmem + c * 32, sr + c * 32);
       tmem_wait_st();
+      if (tw) tr(1 + i, j, 5);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full + 8 * i);
+      if (tw) tr(1 + i, j, 6);
     }
     // ---- epilogue: O_i / l -> fp16 -> swizzled smem (reusing this tile's Q buffer) -> TMA store
     mbar_wait(bar_o_full + 8 * i, 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
-    const uint32_t stage_base = smem_q + i * Cfg::TILE_BYTES + q * 32 * ROWB;  // this warp's 32 rows inside each chunk
+    const uint32_t stage_base = smem_q + i * Cfg::Q_TILE_BYTES + q * 32 * ROWB;  // this warp's 32 rows inside each chunk
 #pragma unroll
     for (int c = 0; c < D / 32; ++c) {
       uint32_t orr[32];
@@ -296,7 +397,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tmem_wait_ld();
       const int chunk = (c * 32) / CW;
       const int sub0 = ((c * 32) % CW) / 8;  // first 16-byte piece inside the smem row
-      const uint32_t row_addr = stage_base + chunk * Cfg::CHUNK_BYTES + lane * ROWB;
+      const uint32_t row_addr = stage_base + chunk * Cfg::Q_CHUNK_BYTES + lane * ROWB;
       const uint32_t xr = (ROWB == 128) ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -311,7 +412,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int row0 = q0 + i * 128 + int(q) * 32;
     if (lane == 0 && row0 < N) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tma_store_3d(&tmO, stage_base + c * Cfg::CHUNK_BYTES, c * CW, row0, bh);
+      for (int c = 0; c < NCH; ++c) tma_store_3d(&tmO, stage_base + c * Cfg::Q_CHUNK_BYTES, c * CW, row0, bh);
       tma_store_commit();
       tma_store_wait_all<0>();
     }
@@ -325,30 +426,39 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
 template <class Cfg>
 static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N, float scale,
-                      cudaStream_t stream, const DeviceInfo& di) {
+                      cudaStream_t stream, const DeviceInfo& di, bool trace = false, int pingpong = 0) {
   constexpr int D = Cfg::D;
   const uint64_t BH = uint64_t(B) * uint64_t(H);
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = make_tmap_3d_u16(&tmQ, Q, BH, N, D, uint64_t(N) * D, D, 1, 128, Cfg::CW, Cfg::ROWB))) return rc;
-  if ((rc = make_tmap_3d_u16(&tmK, K, BH, N, D, uint64_t(N) * D, D, 1, 128, Cfg::CW, Cfg::ROWB))) return rc;
+  if ((rc = make_tmap_3d_u16(&tmK, K, BH, N, D, uint64_t(N) * D, D, 1, Cfg::BC, Cfg::CW, Cfg::ROWB))) return rc;
   if (Cfg::V_DN) {
-    if (N % 8) return set_error(B200K_EALIGN, "b200k_fa2_fwd_f16: V as [B,H,D,N] needs N %% 8 == 0 (16-byte rows), got N=%lld", (long long)N);
+    if (N % 8)
+      return set_error(B200K_EALIGN, "b200k_fa2_fwd_f16: V as [B,H,D,N] needs N %% 8 == 0 (16-byte rows), got N=%lld",
+                       (long long)N);
     rc = make_tmap_3d_u16(&tmV, V, BH, D, N, uint64_t(N) * D, N, 1, D, 64, 128);
   } else {
-    rc = make_tmap_3d_u16(&tmV, V, BH, N, D, uint64_t(N) * D, D, 1, 128, Cfg::CW, Cfg::ROWB);
+    rc = make_tmap_3d_u16(&tmV, V, BH, N, D, uint64_t(N) * D, D, 1, Cfg::BC, Cfg::CW, Cfg::ROWB);
   }
   if (rc) return rc;
   if ((rc = make_tmap_3d_u16(&tmO, O, BH, N, D, uint64_t(N) * D, D, 1, 32, Cfg::CW, Cfg::ROWB))) return rc;
-  auto kern = fa2_fwd_tcgen05_kernel<Cfg>;
+  dim3 grid(unsigned((N + 255) / 256), unsigned(BH));
+  const float scale_log2 = scale * 1.4426950408889634f;
+  if (trace && g_fa2_trace) {
+    auto kern = fa2_fwd_tcgen05_kernel<Cfg, true>;
+    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, g_fa2_trace, pingpong);
+    B200K_CHECK_CUDA(cudaGetLastError());
+    return B200K_OK;
+  }
+  auto kern = fa2_fwd_tcgen05_kernel<Cfg, false>;
   static bool attr_set[64] = {};
   if (!attr_set[di.device]) {
     B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[di.device] = true;
   }
-  dim3 grid(unsigned((N + 255) / 256), unsigned(BH));
-  const float scale_log2 = scale * 1.4426950408889634f;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, nullptr, pingpong);
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;
 }
@@ -358,11 +468,15 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
 extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N,
                                  int64_t D, float scale, int v_is_dn, int variant, void* stream) {
   using namespace b200k;
-  (void)variant;
+  const bool trace = (variant & 0x100) != 0;  // debugging: cycle trace of CTA (0,0), see b200k_debug_set_trace
+  const int pingpong = (variant & 0x200) ? 1 : 0;
   if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_fa2_fwd_f16: null pointer");
   if (B < 1 || H < 1 || N < 1 || N > INT32_MAX || B * H > 65535)
     return set_error(B200K_ESHAPE, "b200k_fa2_fwd_f16: need B,H,N >= 1 and B*H <= 65535 (got B=%lld H=%lld N=%lld)",
                      (long long)B, (long long)H, (long long)N);
+  if (D != 32 && D != 64 && D != 96 && D != 128)
+    return set_error(B200K_EHEADDIM, "headdim not support! (b200k_fa2_fwd_f16: D=%lld, supported 32/64/96/128)",
+                     (long long)D);
   if (scale <= 0.f) scale = 1.0f / sqrtf(float(D));
   DeviceInfo di;
   int rc = get_device_info(&di);
@@ -370,18 +484,23 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (v_is_dn) {
     switch (D) {
-      case 32: return launch_fa2<Fa2Cfg<32, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
-      case 64: return launch_fa2<Fa2Cfg<64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
-      case 96: return launch_fa2<Fa2Cfg<96, 3, true>>(Q, K, V, O, B, H, N, scale, s, di);
-      case 128: return launch_fa2<Fa2Cfg<128, 2, true>>(Q, K, V, O, B, H, N, scale, s, di);
-      default: break;
+      case 32: return launch_fa2<Fa2Cfg<32, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
+      case 64: return launch_fa2<Fa2Cfg<64, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
+      case 96: return launch_fa2<Fa2Cfg<96, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
+      default: return launch_fa2<Fa2Cfg<128, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
     }
   }
   switch (D) {
-    case 32: return launch_fa2<Fa2Cfg<32, 4>>(Q, K, V, O, B, H, N, scale, s, di);
-    case 64: return launch_fa2<Fa2Cfg<64, 4>>(Q, K, V, O, B, H, N, scale, s, di);
-    case 96: return launch_fa2<Fa2Cfg<96, 3>>(Q, K, V, O, B, H, N, scale, s, di);
-    case 128: return launch_fa2<Fa2Cfg<128, 2>>(Q, K, V, O, B, H, N, scale, s, di);
-    default: return set_error(B200K_EHEADDIM, "headdim not support! (b200k_fa2_fwd_f16: D=%lld, supported 32/64/96/128)", (long long)D);
+    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di);
+    case 64: return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
+    case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di);
+    default: return launch_fa2<Fa2Cfg<128, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
   }
+}
+
+// Debug hook (not part of the drop-in surface): device buffer of 3 * 32 * 8 uint64 that the next traced launch
+// (variant | 0x100, D = 64 or 128) fills with clock64() stamps of CTA (0,0).
+extern "C" int b200k_debug_set_trace(void* dev_u64_buffer) {
+  b200k::g_fa2_trace = static_cast<unsigned long long*>(dev_u64_buffer);
+  return B200K_OK;
 }

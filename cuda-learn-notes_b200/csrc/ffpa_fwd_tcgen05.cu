@@ -60,7 +60,7 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t smem_q = base + BAR_BYTES;               // resident Q: nqk boxes
   const uint32_t smem_ring = smem_q + (Q_RESIDENT ? nqk * BOX_BYTES : 0);
 
-  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const uint32_t lane = threadIdx.x & 31;
   const int bh = blockIdx.z;
   const int q0 = blockIdx.x * BR;
@@ -98,15 +98,20 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   if (warp == 0) {
     // ---------------------------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    // (whole warp convergent; one elected lane issues expect_tx + TMA)
+    {
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() {
         if (++stage == stages) { stage = 0; phase ^= 1; }
       };
       if (Q_RESIDENT) {
-        mbar_arrive_expect_tx(bar_q_full, nqk * BOX_BYTES);
-        for (int c = 0; c < nqk; ++c) tma_load_3d(smem_q + c * BOX_BYTES, &tmQ, bar_q_full, c * CW, q0, bh, kPolicyEvictFirst);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_q_full, nqk * BOX_BYTES);
+          for (int c = 0; c < nqk; ++c)
+            tma_load_3d(smem_q + c * BOX_BYTES, &tmQ, bar_q_full, c * CW, q0, bh, kPolicyEvictFirst);
+        }
+        __syncwarp();
       }
       auto load_qk = [&](int j) {
         if (Q_RESIDENT) {
@@ -114,18 +119,24 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             const int nb = min(2, nqk - c);
             const uint32_t dst = smem_ring + stage * STAGE_BYTES;
-            mbar_arrive_expect_tx(bar_full + 8 * stage, nb * BOX_BYTES);
-            for (int b = 0; b < nb; ++b)
-              tma_load_3d(dst + b * BOX_BYTES, &tmK, bar_full + 8 * stage, (c + b) * CW, j * BC, bh, kPolicyEvictLast);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_full + 8 * stage, nb * BOX_BYTES);
+              for (int b = 0; b < nb; ++b)
+                tma_load_3d(dst + b * BOX_BYTES, &tmK, bar_full + 8 * stage, (c + b) * CW, j * BC, bh, kPolicyEvictLast);
+            }
+            __syncwarp();
             advance();
           }
         } else {
           for (int c = 0; c < nqk; ++c) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             const uint32_t dst = smem_ring + stage * STAGE_BYTES;
-            mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * BOX_BYTES);
-            tma_load_3d(dst, &tmQ, bar_full + 8 * stage, c * CW, q0, bh, kPolicyEvictLast);
-            tma_load_3d(dst + BOX_BYTES, &tmK, bar_full + 8 * stage, c * CW, j * BC, bh, kPolicyEvictLast);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * BOX_BYTES);
+              tma_load_3d(dst, &tmQ, bar_full + 8 * stage, c * CW, q0, bh, kPolicyEvictLast);
+              tma_load_3d(dst + BOX_BYTES, &tmK, bar_full + 8 * stage, c * CW, j * BC, bh, kPolicyEvictLast);
+            }
+            __syncwarp();
             advance();
           }
         }
@@ -135,9 +146,12 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const int nb = min(2, nv - c);
           const uint32_t dst = smem_ring + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(bar_full + 8 * stage, nb * BOX_BYTES);
-          for (int b = 0; b < nb; ++b)
-            tma_load_3d(dst + b * BOX_BYTES, &tmV, bar_full + 8 * stage, col0 + (c + b) * CW, j * BC, bh, kPolicyEvictLast);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full + 8 * stage, nb * BOX_BYTES);
+            for (int b = 0; b < nb; ++b)
+              tma_load_3d(dst + b * BOX_BYTES, &tmV, bar_full + 8 * stage, col0 + (c + b) * CW, j * BC, bh, kPolicyEvictLast);
+          }
+          __syncwarp();
           advance();
         }
       };
@@ -148,10 +162,10 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (serial && j + 1 < T) load_qk(j + 1);
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // (whole warp convergent; tcgen05.mma / commit issued by one elected lane)
+    {
       constexpr uint32_t idesc_s = make_idesc_f16(128, BC, true, false, false);
       constexpr uint64_t qk_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);
       constexpr uint64_t v_hi = make_smem_desc_hi(BOX_BYTES, 1024, kSwizzle128B);
@@ -168,14 +182,18 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             tc_fence_after();
             const uint32_t kb = smem_ring + stage * STAGE_BYTES;
             const int nb = min(2, nqk - c);
-            for (int b = 0; b < nb; ++b) {
-              const uint32_t qa = smem_q + (c + b) * BOX_BYTES;
+            if (elect_one()) {
+              for (int b = 0; b < nb; ++b) {
+                const uint32_t qa = smem_q + (c + b) * BOX_BYTES;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_ss<1>(d_tmem, smem_desc(qk_hi, qa + k * 32), smem_desc(qk_hi, kb + b * BOX_BYTES + k * 32), idesc_s,
-                           (c + b + k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  umma_ss<1>(d_tmem, smem_desc(qk_hi, qa + k * 32), smem_desc(qk_hi, kb + b * BOX_BYTES + k * 32),
+                             idesc_s, (c + b + k) != 0 ? 1u : 0u);
+              }
+              umma_commit(bar_empty + 8 * stage);
+              if (c + 2 >= nqk) umma_commit(bar_s_full + 8 * buf);
             }
-            umma_commit(bar_empty + 8 * stage);
+            __syncwarp();
             advance();
           }
         } else {
@@ -184,17 +202,20 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             tc_fence_after();
             const uint32_t qa = smem_ring + stage * STAGE_BYTES;
             const uint32_t kb = qa + BOX_BYTES;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss<1>(d_tmem, smem_desc(qk_hi, qa + k * 32), smem_desc(qk_hi, kb + k * 32), idesc_s,
-                         (c + k) != 0 ? 1u : 0u);
-            umma_commit(bar_empty + 8 * stage);
+              for (int k = 0; k < 4; ++k)
+                umma_ss<1>(d_tmem, smem_desc(qk_hi, qa + k * 32), smem_desc(qk_hi, kb + k * 32), idesc_s,
+                           (c + k) != 0 ? 1u : 0u);
+              umma_commit(bar_empty + 8 * stage);
+              if (c + 1 >= nqk) umma_commit(bar_s_full + 8 * buf);
+            }
+            __syncwarp();
             advance();
           }
         }
-        umma_commit(bar_s_full + 8 * buf);
       };
-      auto issue_pv = [&](int buf, bool accumulate) {
+      auto issue_pv = [&](int buf, bool accumulate, bool last_tile) {
         const uint32_t p_tmem = tmem_base + (buf ? S_COL1 : S_COL0);
         for (int c = 0; c < nv; c += 2) {
           mbar_wait(bar_full + 8 * stage, phase);
@@ -203,10 +224,18 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           const uint32_t va = smem_ring + stage * STAGE_BYTES;
           const uint32_t idesc_o = make_idesc_f16(128, uint32_t(nb * CW), true, false, true);
           const uint32_t d_tmem = tmem_base + O_COL + c * CW;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BC / 16; ++k)
-            umma_ts<1>(d_tmem, p_tmem + k * 8, smem_desc(v_hi, va + k * 16 * 128), idesc_o, (accumulate || k != 0) ? 1u : 0u);
-          umma_commit(bar_empty + 8 * stage);
+            for (int k = 0; k < BC / 16; ++k)
+              umma_ts<1>(d_tmem, p_tmem + k * 8, smem_desc(v_hi, va + k * 16 * 128), idesc_o,
+                         (accumulate || k != 0) ? 1u : 0u);
+            umma_commit(bar_empty + 8 * stage);
+            if (c + 2 >= nv) {  // whole PV_j issued
+              umma_commit(bar_pv_done);
+              if (last_tile) umma_commit(bar_o_full);
+            }
+          }
+          __syncwarp();
           advance();
         }
       };
@@ -219,13 +248,10 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (!serial && j + 1 < T) issue_s((j + 1) & 1);
         mbar_wait(bar_p_full + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
-        issue_pv(j & 1, j > 0);
-        umma_commit(bar_pv_done);
-        if (j == T - 1) umma_commit(bar_o_full);
+        issue_pv(j & 1, j > 0, j == T - 1);
         if (serial && j + 1 < T) issue_s((j + 1) & 1);  // debugging order: no QK^T / softmax overlap
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ---------------------------------------------------------------------------------- softmax + epilogue
     const uint32_t q = warp & 3;
@@ -285,17 +311,28 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tmem_wait_st();
         }
       }
-      float l0 = 0.f, l1 = 0.f;
+      // processed in blocks of 16: all FFMAs, then all MUFU.EX2, then sums / packs, so that 16 independent
+      // exponentials are in flight per thread (the MUFU pipe is the bound of this loop)
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       const float neg_m = -m_ref;
 #pragma unroll
-      for (int c = 0; c < 128; c += 2) {
-        const float p0 = fast_exp2(fmaf(s[c], scale_log2, neg_m));
-        const float p1 = fast_exp2(fmaf(s[c + 1], scale_log2, neg_m));
-        l0 += p0;
-        l1 += p1;
-        sr[c >> 1] = pack_half2(p0, p1);
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        float x[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) x[e] = fmaf(s[c0 + e], scale_log2, neg_m);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) x[e] = fast_exp2(x[e]);
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          l0 += x[e];
+          l1 += x[e + 1];
+          l2 += x[e + 2];
+          l3 += x[e + 3];
+          sr[(c0 + e) >> 1] = pack_half2(x[e], x[e + 1]);
+          sr[((c0 + e) >> 1) + 1] = pack_half2(x[e + 2], x[e + 3]);
+        }
       }
-      l += l0 + l1;
+      l += (l0 + l1) + (l2 + l3);
       tmem_st_32x32b_x32(s_tmem, sr);
       tmem_st_32x32b_x32(s_tmem + 32, sr + 32);
       tmem_wait_st();

