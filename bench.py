@@ -256,6 +256,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device. The product path has no CPU fallback; use --impl reference for the CPU arm.")
     torch.cuda.set_device(local_rank)
     if dist_on:
+        os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout; keep stdout = one JSON line
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -26,11 +26,14 @@
 
 namespace b200k {
 
-template <int D_, int BC_, int STAGES_, bool V_DN_ = false>
+template <int D_, int BC_, int STAGES_, bool V_DN_ = false, bool ALIAS_P_ = false>
 struct Fa2Cfg {
   static constexpr int D = D_;
   static constexpr int BC = BC_;                       // keys per KV tile
   static constexpr int STAGES = STAGES_;
+  // ALIAS_P: P overwrites the first BC/2 columns of S (needed when S0 S1 O0 O1 already fill the 512 columns, i.e.
+  // D = 128 with BC = 128).  S_i(j+1) can then only be issued after PV_i(j), as in-order tcgen05 execution protects P.
+  static constexpr bool ALIAS_P = ALIAS_P_;
   static constexpr bool V_DN = V_DN_;  // V passed transposed as [B,H,D,N] (the reference's *_swizzle_qkv entry points)
   static constexpr int CW = (D % 64 == 0) ? 64 : 32;  // width of one smem chunk along D (elements)
   static constexpr int NCH = D / CW;
@@ -44,13 +47,13 @@ struct Fa2Cfg {
   static constexpr int BAR_BYTES = 1024;
   static constexpr int SMEM_BYTES = 1024 + BAR_BYTES + 2 * Q_TILE_BYTES + 2 * STAGES * KV_TILE_BYTES;
   static constexpr int S_COL0 = 0, S_COL1 = BC;
-  static constexpr int P_COL0 = 2 * BC, P_COL1 = 2 * BC + BC / 2;
-  static constexpr int O_COL0 = 3 * BC, O_COL1 = 3 * BC + D;
+  static constexpr int P_COL0 = ALIAS_P ? S_COL0 : 2 * BC, P_COL1 = ALIAS_P ? S_COL1 : 2 * BC + BC / 2;
+  static constexpr int O_COL0 = ALIAS_P ? 2 * BC : 3 * BC, O_COL1 = O_COL0 + D;
   static constexpr int TMEM_COLS = 512;
   static constexpr int THREADS = 384;
   static_assert(D % 32 == 0 && D >= 32 && D <= 128, "head dim");
   static_assert(BC == 64 || BC == 128, "keys per tile");
-  static_assert(3 * BC + 2 * D <= 512, "TMEM columns");
+  static_assert((ALIAS_P ? 2 : 3) * BC + 2 * D <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 232448, "smem");
 };
 
@@ -247,6 +250,27 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_after();
       issue_s(1, 0, bar_s_full + 8, bar_k_empty);
       for (int j = 0; j < T; ++j) {
+        if constexpr (Cfg::ALIAS_P) {
+          // P lives in the S columns: PV_i(j) first, then S_i(j+1) (in-order execution keeps P intact until read)
+          const int s = j % STAGES;
+          const int s1 = (j + 1) % STAGES;
+          mbar_wait(bar_v_full + 8 * s, (j / STAGES) & 1);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            mbar_wait(bar_p_full + 8 * i, j & 1);
+            tc_fence_after();
+            issue_pv(i, s, j > 0, bar_p_free + 8 * i, (j == T - 1) ? bar_o_full + 8 * i : 0u,
+                     i == 1 ? bar_v_empty + 8 * s : 0u);
+            if (j + 1 < T) {
+              if (i == 0) {
+                mbar_wait(bar_k_full + 8 * s1, ((j + 1) / STAGES) & 1);
+                tc_fence_after();
+              }
+              issue_s(i, s1, bar_s_full + 8 * i, i == 1 ? bar_k_empty + 8 * s1 : 0u);
+            }
+          }
+          continue;
+        }
         if (j + 1 < T) {
           // scores of the next KV tile: only needs the S columns back (the softmax warps hold tile j in registers)
           const int s1 = (j + 1) % STAGES;
@@ -299,9 +323,11 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tmem_wait_ld();
       if (tw) tr(1 + i, j, 1);
       // the scores are in registers: give the S columns back so that S(j+1) is computed under this softmax
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_s_free + 8 * i);
+      if constexpr (!Cfg::ALIAS_P) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_s_free + 8 * i);
+      }
       float* s = reinterpret_cast<float*>(sr);
       if (j == T - 1 && (N % BC) != 0) {
         const int valid = N - j * BC;
@@ -487,14 +513,16 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
       case 32: return launch_fa2<Fa2Cfg<32, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
       case 64: return launch_fa2<Fa2Cfg<64, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
       case 96: return launch_fa2<Fa2Cfg<96, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
-      default: return launch_fa2<Fa2Cfg<128, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
+      default: return launch_fa2<Fa2Cfg<128, 128, 2, true, true>>(Q, K, V, O, B, H, N, scale, s, di);
     }
   }
   switch (D) {
     case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di);
     case 64: return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
     case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di);
-    default: return launch_fa2<Fa2Cfg<128, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
+    default:
+      if (variant & 0x400) return launch_fa2<Fa2Cfg<128, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
+      return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
   }
 }
 

@@ -21,7 +21,9 @@ for (B, H, N, D) in ((4, 48, 8192, 64), (4, 64, 8192, 128)):
     o = torch.empty_like(q)
     fl = 4.0 * B * H * N * N * D
     for rep in range(3):
-        for variant, name in ((0, "plain"), (0x200, "pingpong")):
+        for variant, name in ((0, "plain"), (0x200, "pingpong"), (0x400, "bc64"), (0x600, "bc64+pingpong")):
+            if D != 128 and variant & 0x400:
+                continue
             t = timeit(lambda: ops.fa2_fwd(q, k, v, o, variant=variant))
             print("D=%d %s: %.3f ms %.0f TFLOPS" % (D, name, t, fl / t * 1e-9), flush=True)
     for variant, name in ((0x100, "plain"), (0x300, "pingpong")):
