@@ -88,8 +88,9 @@ def hgemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, tn: bool = False, v
     if b.size(0) != K or c.size(0) != M or c.size(1) != N:
         raise RuntimeError("Tensor size mismatch!")
     if tn:
-        bt = b.t()  # [N,K]; must be the contiguous storage
-        _check_cuda_contig(a, bt, c)
+        # Two spellings of "storage is B^T [N,K] row-major": the reference's as_col_major() returns a CONTIGUOUS
+        # [K,N]-shaped tensor holding B^T's elements (tools/utils.py:L135-140); a strided view b = Bt.t() is the other.
+        _check_cuda_contig(a, b if b.is_contiguous() else b.t(), c)
     else:
         _check_cuda_contig(a, b, c)
     with _DeviceGuard(a):

@@ -20,6 +20,8 @@ def _namespaces():
     import toy_hgemm
 
     table = dict(support_libs.BY_LOAD_NAME)
+    for alias, name in support_libs.LOAD_NAME_ALIASES.items():
+        table[alias] = table[name]
     table["flash_attn_lib"] = flash_attn_lib
     table["hgemm_lib"] = toy_hgemm
     return table

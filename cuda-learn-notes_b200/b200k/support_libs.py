@@ -137,3 +137,6 @@ BY_LOAD_NAME = {
     "elementwise_lib": elementwise_lib, "block_all_reduce_lib": reduce_lib, "softmax_lib": softmax_lib,
     "rms_norm_lib": rms_norm_lib, "rope_lib": rope_lib, "hist_lib": hist_lib, "embedding_lib": embedding_lib,
 }
+# rope.py and embedding.py call load(name="rope") / load(name="embedding") (kernels/rope/rope.py:L13-15,
+# kernels/embedding/embedding.py:L11-13)
+LOAD_NAME_ALIASES = {"rope": "rope_lib", "embedding": "embedding_lib"}

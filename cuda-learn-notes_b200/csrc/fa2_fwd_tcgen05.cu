@@ -330,6 +330,9 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       float* s = reinterpret_cast<float*>(sr);
       if (j == T - 1 && (N % BC) != 0) {
+        // ragged last tile only.  The empty asm keeps this a real (warp-uniform) branch: if-converted, the 2 x BC
+        // compare/select instructions would run on every tile.
+        asm volatile("" ::: "memory");
         const int valid = N - j * BC;
 #pragma unroll
         for (int c = 0; c < BC; ++c)
@@ -376,7 +379,8 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       // processed in blocks of 16: all FFMAs, then all MUFU.EX2, then sums / packs, so that 16 independent
       // exponentials are in flight per thread (the MUFU pipe is the bound of this loop)
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      const float neg_m = -m_ref;
+      float neg_m = -m_ref;
+      if (pingpong) asm volatile("" : "+f"(neg_m));  // pins the exponentials behind the turn-taking barrier
 #pragma unroll
       for (int c0 = 0; c0 < BC; c0 += 16) {
         float x[16];
@@ -495,7 +499,9 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
                                  int64_t D, float scale, int v_is_dn, int variant, void* stream) {
   using namespace b200k;
   const bool trace = (variant & 0x100) != 0;  // debugging: cycle trace of CTA (0,0), see b200k_debug_set_trace
-  const int pingpong = (variant & 0x200) ? 1 : 0;
+  // exp2-phase turn-taking between the two softmax warpgroups: measured +4% at D=64 (MUFU-bound), -1..2% at D=128
+  // (tensor/smem-bound), profiles/r01_fa2_variants.txt.  variant bit 0x200 flips the default.
+  const int pingpong = ((D <= 64) ? 1 : 0) ^ ((variant & 0x200) ? 1 : 0);
   if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_fa2_fwd_f16: null pointer");
   if (B < 1 || H < 1 || N < 1 || N > INT32_MAX || B * H > 65535)
     return set_error(B200K_ESHAPE, "b200k_fa2_fwd_f16: need B,H,N >= 1 and B*H <= 65535 (got B=%lld H=%lld N=%lld)",
@@ -517,7 +523,7 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
     }
   }
   switch (D) {
-    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di);
+    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, false, pingpong);
     case 64: return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
     case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di);
     default:

@@ -272,6 +272,9 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tmem_wait_ld();
       float* s = reinterpret_cast<float*>(sr);
       if (j == T - 1 && (N % BC) != 0) {
+        // ragged last tile only.  The empty asm keeps this a real (warp-uniform) branch: if-converted, the 2 x BC
+        // compare/select instructions would run on every tile.
+        asm volatile("" ::: "memory");
         const int valid = N - j * BC;
 #pragma unroll
         for (int c = 0; c < 128; ++c)

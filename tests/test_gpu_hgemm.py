@@ -58,6 +58,8 @@ def test_hgemm_drop_in_names_route_to_kernel():
         c = torch.zeros(256, 384, dtype=torch.half, device="cuda")
         fn = getattr(toy_hgemm, name)
         bb = b_col_major if ("_tn" in name) else b
+        if name.endswith("_tn_cute"):  # the reference script's own spelling: contiguous [K,N]-shaped buffer of B^T
+            bb = b.t().reshape(b.shape).contiguous()
         if "stages" in name:
             fn(a, bb, c, 3, True, 2048)
         else:
