@@ -66,7 +66,7 @@ constexpr float kRescaleThreshold = 8.0f;
 constexpr int kTraceIters = 32, kTraceEvents = 8;
 static unsigned long long* g_fa2_trace = nullptr;  // set through b200k_debug_set_trace()
 
-template <class Cfg, bool TRACE>
+template <class Cfg, bool TRACE, bool POLY>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int N,
@@ -376,29 +376,32 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (pingpong) named_bar_sync(1 + i, 256);
       if (tw) tr(1 + i, j, 2);
       // P = exp2(s * scale_log2 - m_ref), row sum in fp32, P packed to fp16 pairs in place
-      // processed in blocks of 16: all FFMAs, then all MUFU.EX2, then sums / packs, so that 16 independent
-      // exponentials are in flight per thread (the MUFU pipe is the bound of this loop)
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      // processed in blocks of 16 with packed fp32x2 arithmetic (FFMA2 / FADD2: one issue slot per two elements);
+      // all FFMA2s of a block, then its MUFU.EX2s, then sums / packs, so 16 independent exponentials are in flight
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
       float neg_m = -m_ref;
       if (pingpong) asm volatile("" : "+f"(neg_m));  // pins the exponentials behind the turn-taking barrier
+      const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(neg_m, neg_m);
 #pragma unroll
       for (int c0 = 0; c0 < BC; c0 += 16) {
-        float x[16];
+        float2 x[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) x[e] = fmaf(s[c0 + e], scale_log2, neg_m);
+        for (int e = 0; e < 8; ++e) x[e] = ffma2(make_float2(s[c0 + 2 * e], s[c0 + 2 * e + 1]), scale2, negm2);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) x[e] = fast_exp2(x[e]);
+        for (int e = 0; e < 8; ++e) {
+          x[e].x = fast_exp2(x[e].x);
+          // every 4th exponential is evaluated on the FMA pipe (exp2_poly3) when requested
+          x[e].y = (POLY && (e & 1)) ? exp2_poly3(x[e].y) : fast_exp2(x[e].y);
+        }
 #pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          l0 += x[e];
-          l1 += x[e + 1];
-          l2 += x[e + 2];
-          l3 += x[e + 3];
-          sr[(c0 + e) >> 1] = pack_half2(x[e], x[e + 1]);
-          sr[((c0 + e) >> 1) + 1] = pack_half2(x[e + 2], x[e + 3]);
+        for (int e = 0; e < 8; e += 2) {
+          acc0 = fadd2(acc0, x[e]);
+          acc1 = fadd2(acc1, x[e + 1]);
+          sr[(c0 >> 1) + e] = pack_half2(x[e].x, x[e].y);
+          sr[(c0 >> 1) + e + 1] = pack_half2(x[e + 1].x, x[e + 1].y);
         }
       }
-      l += (l0 + l1) + (l2 + l3);
+      l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
       if (pingpong) named_bar_arrive(2 - i, 256);
       if (tw) tr(1 + i, j, 3);
       if (!pv_done) {  // P_i(j-1) must have been consumed before it is overwritten (normally long since true)
@@ -456,7 +459,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
 template <class Cfg>
 static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N, float scale,
-                      cudaStream_t stream, const DeviceInfo& di, bool trace = false, int pingpong = 0) {
+                      cudaStream_t stream, const DeviceInfo& di, bool trace = false, int pingpong = 0, bool poly = false) {
   constexpr int D = Cfg::D;
   const uint64_t BH = uint64_t(B) * uint64_t(H);
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -475,14 +478,21 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
   if ((rc = make_tmap_3d_u16(&tmO, O, BH, N, D, uint64_t(N) * D, D, 1, 32, Cfg::CW, Cfg::ROWB))) return rc;
   dim3 grid(unsigned((N + 255) / 256), unsigned(BH));
   const float scale_log2 = scale * 1.4426950408889634f;
+  if (poly && Cfg::D <= 64 && !Cfg::V_DN) {
+    auto kern = fa2_fwd_tcgen05_kernel<Cfg, false, (Cfg::D <= 64 && !Cfg::V_DN)>;
+    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, nullptr, pingpong);
+    B200K_CHECK_CUDA(cudaGetLastError());
+    return B200K_OK;
+  }
   if (trace && g_fa2_trace) {
-    auto kern = fa2_fwd_tcgen05_kernel<Cfg, true>;
+    auto kern = fa2_fwd_tcgen05_kernel<Cfg, true, false>;
     B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, g_fa2_trace, pingpong);
     B200K_CHECK_CUDA(cudaGetLastError());
     return B200K_OK;
   }
-  auto kern = fa2_fwd_tcgen05_kernel<Cfg, false>;
+  auto kern = fa2_fwd_tcgen05_kernel<Cfg, false, false>;
   static bool attr_set[64] = {};
   if (!attr_set[di.device]) {
     B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -499,9 +509,13 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
                                  int64_t D, float scale, int v_is_dn, int variant, void* stream) {
   using namespace b200k;
   const bool trace = (variant & 0x100) != 0;  // debugging: cycle trace of CTA (0,0), see b200k_debug_set_trace
-  // exp2-phase turn-taking between the two softmax warpgroups: measured +4% at D=64 (MUFU-bound), -1..2% at D=128
-  // (tensor/smem-bound), profiles/r01_fa2_variants.txt.  variant bit 0x200 flips the default.
-  const int pingpong = ((D <= 64) ? 1 : 0) ^ ((variant & 0x200) ? 1 : 0);
+  // Experiment switches (measurements in profiles/r01_fa2_variants.txt, B200, (4,48,8192,64)):
+  //   0x200 exp2-phase turn-taking between the two softmax warpgroups: +4% before the packed-math rewrite of the
+  //         softmax loop, -2% after it (758 vs 773 TFLOP/s) -> off by default;
+  //   0x800 25% of the exponentials as a degree-3 polynomial on the FMA pipe: 712 vs 773 TFLOP/s (the loop is
+  //         issue-bound, not MUFU-bound) -> off by default.
+  const int pingpong = (variant & 0x200) ? 1 : 0;
+  const bool poly = (variant & 0x800) != 0;
   if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_fa2_fwd_f16: null pointer");
   if (B < 1 || H < 1 || N < 1 || N > INT32_MAX || B * H > 65535)
     return set_error(B200K_ESHAPE, "b200k_fa2_fwd_f16: need B,H,N >= 1 and B*H <= 65535 (got B=%lld H=%lld N=%lld)",
@@ -523,8 +537,8 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
     }
   }
   switch (D) {
-    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, false, pingpong);
-    case 64: return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
+    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, false, pingpong, poly);
+    case 64: return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong, poly);
     case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di);
     default:
       if (variant & 0x400) return launch_fa2<Fa2Cfg<128, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);

@@ -314,28 +314,30 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tmem_wait_st();
         }
       }
-      // processed in blocks of 16: all FFMAs, then all MUFU.EX2, then sums / packs, so that 16 independent
-      // exponentials are in flight per thread (the MUFU pipe is the bound of this loop)
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      const float neg_m = -m_ref;
+      // processed in blocks of 16 with packed fp32x2 arithmetic (FFMA2 / FADD2: one issue slot per two elements);
+      // all FFMA2s of a block, then its MUFU.EX2s, then sums / packs, so 16 independent exponentials are in flight
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+      float neg_m = -m_ref;
+      const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(neg_m, neg_m);
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 16) {
-        float x[16];
+        float2 x[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) x[e] = fmaf(s[c0 + e], scale_log2, neg_m);
+        for (int e = 0; e < 8; ++e) x[e] = ffma2(make_float2(s[c0 + 2 * e], s[c0 + 2 * e + 1]), scale2, negm2);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) x[e] = fast_exp2(x[e]);
+        for (int e = 0; e < 8; ++e) {
+          x[e].x = fast_exp2(x[e].x);
+          x[e].y = fast_exp2(x[e].y);
+        }
 #pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          l0 += x[e];
-          l1 += x[e + 1];
-          l2 += x[e + 2];
-          l3 += x[e + 3];
-          sr[(c0 + e) >> 1] = pack_half2(x[e], x[e + 1]);
-          sr[((c0 + e) >> 1) + 1] = pack_half2(x[e + 2], x[e + 3]);
+        for (int e = 0; e < 8; e += 2) {
+          acc0 = fadd2(acc0, x[e]);
+          acc1 = fadd2(acc1, x[e + 1]);
+          sr[(c0 >> 1) + e] = pack_half2(x[e].x, x[e].y);
+          sr[(c0 >> 1) + e + 1] = pack_half2(x[e + 1].x, x[e + 1].y);
         }
       }
-      l += (l0 + l1) + (l2 + l3);
+      l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
       tmem_st_32x32b_x32(s_tmem, sr);
       tmem_st_32x32b_x32(s_tmem + 32, sr + 32);
       tmem_wait_st();

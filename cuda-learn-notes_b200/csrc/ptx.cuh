@@ -362,4 +362,37 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Blackwell packed fp32x2 arithmetic (FFMA2 / FADD2): two fp32 lanes per instruction and issue slot.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  ra = (unsigned long long)__float_as_uint(a.x) | ((unsigned long long)__float_as_uint(a.y) << 32);
+  rb = (unsigned long long)__float_as_uint(b.x) | ((unsigned long long)__float_as_uint(b.y) << 32);
+  rc = (unsigned long long)__float_as_uint(c.x) | ((unsigned long long)__float_as_uint(c.y) << 32);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return make_float2(__uint_as_float((unsigned)rd), __uint_as_float((unsigned)(rd >> 32)));
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  ra = (unsigned long long)__float_as_uint(a.x) | ((unsigned long long)__float_as_uint(a.y) << 32);
+  rb = (unsigned long long)__float_as_uint(b.x) | ((unsigned long long)__float_as_uint(b.y) << 32);
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return make_float2(__uint_as_float((unsigned)rd), __uint_as_float((unsigned)(rd >> 32)));
+}
+
+// 2^x on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for
+// 2^f (max relative error 1.0e-4, below the 4.9e-4 rounding step of the fp16 P it feeds), exponent patched in with
+// an integer multiply-add.  Used for a fraction of the softmax exponentials so that the MUFU pipe (16 ex2/clk/SM) is
+// not the only source of exponentials (the FlashAttention-4 trick).
+__device__ __forceinline__ float exp2_poly3(float x) {
+  x = fmaxf(x, -126.0f);                       // also maps -inf (masked keys) to 2^-126 -> 0 in fp16
+  const float magic = 12582912.0f;             // 1.5 * 2^23: x + magic has round(x) in its low mantissa bits
+  const float t = x + magic;
+  const float f = x - (t - magic);
+  float p = fmaf(f, 5.500892858e-02f, 2.422109601e-01f);
+  p = fmaf(p, f, 6.932829276e-01f);
+  p = fmaf(p, f, 1.0f);
+  // (bits(t) << 23) == n << 23 (mod 2^32): the low 9 bits of bits(magic) are zero
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 }  // namespace b200k
