@@ -347,16 +347,20 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mx3 = fmaxf(mx3, s[c + 3]);
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-      bool pv_done = (j == 0);  // has PV_i(j-1) been observed complete (O_i stable, P_i columns free)?
+      // Has PV_i(j-1) been observed complete (O_i stable, P_i columns free)?  With ALIAS_P it always has: S_i(j) was
+      // issued after PV_i(j-1) and tcgen05.commit covers all prior MMAs, so s_full(j) already implies it.
+      bool pv_done = (j == 0) || Cfg::ALIAS_P;
       if (j == 0) {
         m_ref = mx;
       } else {
         const bool need = mx > m_ref + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
           // warp-uniform: rescale this warp's 32 rows of O (rows that did not move use alpha = 1)
-          mbar_wait(bar_p_free + 8 * i, (j - 1) & 1);
-          tc_fence_after();
-          pv_done = true;
+          if (!pv_done) {
+            mbar_wait(bar_p_free + 8 * i, (j - 1) & 1);
+            tc_fence_after();
+            pv_done = true;
+          }
           const float m_new = need ? mx : m_ref;
           const float alpha = fast_exp2(m_ref - m_new);
           m_ref = m_new;

@@ -382,6 +382,10 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   if (warp == 2) tmem_dealloc<1>(tmem_base, ffpa::TMEM_COLS);
 }
 
+// CTA-pair variant for D % 256 == 0 (ffpa2_fwd_tcgen05.cu)
+int launch_ffpa_2cta(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N, int64_t D,
+                     float scale, cudaStream_t s);
+
 }  // namespace b200k
 
 extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N,
@@ -400,6 +404,11 @@ extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, v
   int rc = get_device_info(&di);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // variant bits: 1 = force the single-CTA kernel, 2 = stream Q even when it fits, 4 = serial debug order
+  // CTA-pair kernel for D = 512 / 768 / 1024 (measured on (1,32,4096,D): D=512 994 vs 836 TFLOP/s; at D=256 the
+  // single-CTA kernel is ahead, 1.21 vs 1.16 PFLOP/s — profiles/r01_ffpa_check.jsonl); variant bit 8 forces it.
+  if ((D % 256) == 0 && (D >= 512 || (variant & 8)) && !(variant & 7))
+    return launch_ffpa_2cta(Q, K, V, O, B, H, N, D, scale, s);
   const uint64_t BH = uint64_t(B) * uint64_t(H);
   CUtensorMap tmQ, tmK, tmV, tmO;
   if ((rc = make_tmap_3d_u16(&tmQ, Q, BH, N, D, uint64_t(N) * D, D, 1, 128, 64, 128))) return rc;
