@@ -25,21 +25,27 @@ namespace ffpa {
 constexpr int BR = 128, BC = 128, CW = 64;
 constexpr int BOX_BYTES = 128 * 128;      // [128 rows x 64 fp16], 128B-swizzled
 constexpr int STAGE_BYTES = 2 * BOX_BYTES;  // a ring stage holds two boxes
-constexpr int BAR_BYTES = 1024;
+constexpr int BAR_BYTES = 3072;  // 1 KB of mbarriers + 2 KB exchange buffer of the split-row softmax
 constexpr int MAX_STAGES = 6;
 constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256;
 constexpr int TMEM_COLS = 512;
-constexpr int THREADS = 256;
 constexpr float kRescaleThreshold = 8.0f;
 }  // namespace ffpa
 
 // Q_RESIDENT: the whole [128 x D] Q tile is loaded once; ring stages then carry {K chunk c, K chunk c+1} for QK^T.
 // Otherwise ring stages carry {Q chunk c, K chunk c}.  PV stages carry {V chunk c, V chunk c+1} of this CTA's slice.
-template <bool Q_RESIDENT>
-__global__ void __launch_bounds__(ffpa::THREADS, 1)
+// SPLIT = 2: two softmax warpgroups share every query row (columns 0..63 / 64..127 of the score tile): warps 4..7 and
+// 8..11 with the same TMEM lane quadrant work on the same 32 rows.  Partial row maxima are exchanged through shared
+// memory (one named barrier of 64 threads per quadrant and tile); row sums stay partial until the epilogue.  This halves
+// the softmax time per tile, which is what bounds the kernel when D is small (D = 128: QK^T + PV need ~1150 cycles per
+// tile, one warpgroup of exponentials ~2250).
+template <bool Q_RESIDENT, int SPLIT>
+__global__ void __launch_bounds__(128 + 128 * SPLIT, 1)
 ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int N, int D,
                         int slice_cols, int stages, float scale_log2, int serial) {
+  const int dbg_skip = serial >> 1;  // debugging: 1 = skip the exponentials, 2 = skip all softmax work (timing probes)
+  serial &= 1;
   using namespace ffpa;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -56,6 +62,7 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t bar_o_full = bar_pv_done + 8;           // 1   completes once, after the last PV (epilogue)
   const uint32_t tmem_slot = bar_o_full + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
+  float* xch = reinterpret_cast<float*>(base_ptr + 1024);  // [2 tile parities][2 halves][128 rows] fp32 (SPLIT = 2)
   const int nqk = D / CW;                                 // 64-wide chunks of the head dim
   const uint32_t smem_q = base + BAR_BYTES;               // resident Q: nqk boxes
   const uint32_t smem_ring = smem_q + (Q_RESIDENT ? nqk * BOX_BYTES : 0);
@@ -81,8 +88,8 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(bar_q_full, 1);
     mbar_init(bar_s_full, 1);
     mbar_init(bar_s_full + 8, 1);
-    mbar_init(bar_p_full, 4);
-    mbar_init(bar_p_full + 8, 4);
+    mbar_init(bar_p_full, 4 * SPLIT);
+    mbar_init(bar_p_full + 8, 4 * SPLIT);
     mbar_init(bar_pv_done, 1);
     mbar_init(bar_o_full, 1);
     fence_mbar_init();
@@ -254,7 +261,10 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------------------------- softmax + epilogue
-    const uint32_t q = warp & 3;
+    constexpr int COLS = 128 / SPLIT;                    // score columns handled by one thread
+    const uint32_t q = warp & 3;                         // TMEM lane quadrant = which 32 query rows
+    const uint32_t half = (SPLIT == 2) ? ((warp - 4) >> 2) : 0u;  // which column half of the score tile
+    const uint32_t row = q * 32 + lane;
     const uint32_t lane_base = (q * 32) << 16;
     const uint32_t o_tmem = tmem_base + lane_base + O_COL;
     float m_ref = -INFINITY;
@@ -264,31 +274,44 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const uint32_t s_tmem = tmem_base + lane_base + (buf ? S_COL1 : S_COL0);
       mbar_wait(bar_s_full + 8 * buf, (j >> 1) & 1);
       tc_fence_after();
-      uint32_t sr[128];
-      tmem_ld_32x32b_x32(s_tmem, sr);
-      tmem_ld_32x32b_x32(s_tmem + 32, sr + 32);
-      tmem_ld_32x32b_x32(s_tmem + 64, sr + 64);
-      tmem_ld_32x32b_x32(s_tmem + 96, sr + 96);
+      if (dbg_skip == 2) {  // timing probe: hand the (garbage) P back at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_full + 8 * buf);
+        l = 1.f;
+        continue;
+      }
+      uint32_t sr[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS / 32; ++c) tmem_ld_32x32b_x32(s_tmem + half * COLS + c * 32, sr + c * 32);
       tmem_wait_ld();
       float* s = reinterpret_cast<float*>(sr);
       if (j == T - 1 && (N % BC) != 0) {
         // ragged last tile only.  The empty asm keeps this a real (warp-uniform) branch: if-converted, the 2 x BC
         // compare/select instructions would run on every tile.
         asm volatile("" ::: "memory");
-        const int valid = N - j * BC;
+        const int valid = N - j * BC - int(half) * COLS;
 #pragma unroll
-        for (int c = 0; c < 128; ++c)
+        for (int c = 0; c < COLS; ++c)
           if (c >= valid) s[c] = -INFINITY;
       }
       float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-      for (int c = 4; c < 128; c += 4) {
+      for (int c = 4; c < COLS; c += 4) {
         mx0 = fmaxf(mx0, s[c]);
         mx1 = fmaxf(mx1, s[c + 1]);
         mx2 = fmaxf(mx2, s[c + 2]);
         mx3 = fmaxf(mx3, s[c + 3]);
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if constexpr (SPLIT == 2) {
+        // row max over both halves: both threads of a row end up with the identical value
+        float* slot = xch + (j & 1) * 256;
+        slot[half * 128 + row] = mx;
+        named_bar_sync(1 + q, 64);
+        mx = fmaxf(mx, slot[(half ^ 1) * 128 + row]);
+      }
+      mx *= scale_log2;
       if (j == 0) {
         m_ref = mx;
       } else {
@@ -303,13 +326,17 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           const float alpha = fast_exp2(m_ref - m_new);
           m_ref = m_new;
           l *= alpha;
-          for (int c = 0; c < ncols / 16; ++c) {
-            uint32_t orr[16];
-            tmem_ld_32x32b_x16(o_tmem + c * 16, orr);
-            tmem_wait_ld();
+          // with SPLIT = 2 the two threads of a row rescale alternate 64-column chunks of O
+          for (int cc = int(half); cc < nv; cc += SPLIT) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
-            tmem_st_32x32b_x16(o_tmem + c * 16, orr);
+            for (int c = 0; c < 4; ++c) {
+              uint32_t orr[16];
+              tmem_ld_32x32b_x16(o_tmem + cc * 64 + c * 16, orr);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
+              tmem_st_32x32b_x16(o_tmem + cc * 64 + c * 16, orr);
+            }
           }
           tmem_wait_st();
         }
@@ -320,14 +347,16 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       float neg_m = -m_ref;
       const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(neg_m, neg_m);
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 16) {
+      for (int c0 = 0; c0 < COLS; c0 += 16) {
         float2 x[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[e] = ffma2(make_float2(s[c0 + 2 * e], s[c0 + 2 * e + 1]), scale2, negm2);
+        if (dbg_skip != 1) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          x[e].x = fast_exp2(x[e].x);
-          x[e].y = fast_exp2(x[e].y);
+          for (int e = 0; e < 8; ++e) {
+            x[e].x = fast_exp2(x[e].x);
+            x[e].y = fast_exp2(x[e].y);
+          }
         }
 #pragma unroll
         for (int e = 0; e < 8; e += 2) {
@@ -338,39 +367,48 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
       l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
-      tmem_st_32x32b_x32(s_tmem, sr);
-      tmem_st_32x32b_x32(s_tmem + 32, sr + 32);
+#pragma unroll
+      for (int c = 0; c < COLS / 64; ++c) tmem_st_32x32b_x32(s_tmem + half * (COLS / 2) + c * 32, sr + c * 32);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full + 8 * buf);
     }
     // ---- epilogue
+    if constexpr (SPLIT == 2) {
+      // total row sum = the two partial sums (the slot of parity T&1 was last used at tile T-2: free again)
+      float* slot = xch + (T & 1) * 256;
+      slot[half * 128 + row] = l;
+      named_bar_sync(1 + q, 64);
+      l += slot[(half ^ 1) * 128 + row];
+    }
     mbar_wait(bar_o_full, 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const uint32_t stage_base = smem_ring + q * 32 * 128;  // ring memory is idle now: [chunk][128 rows][128 B]
-    for (int c = 0; c < ncols / 32; ++c) {
-      uint32_t orr[32];
-      tmem_ld_32x32b_x32(o_tmem + c * 32, orr);
-      tmem_wait_ld();
-      const int chunk = c >> 1;
-      const int sub0 = (c & 1) * 4;
-      const uint32_t row_addr = stage_base + chunk * BOX_BYTES + lane * 128;
-      const uint32_t xr = lane & 7;
+    for (int cc = int(half); cc < nv; cc += SPLIT) {        // 64-column chunks of O owned by this thread
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float* f = reinterpret_cast<const float*>(orr + 8 * g);
-        st_shared_v4(row_addr + (((sub0 + g) ^ xr) << 4), pack_half2(f[0] * inv_l, f[1] * inv_l),
-                     pack_half2(f[2] * inv_l, f[3] * inv_l), pack_half2(f[4] * inv_l, f[5] * inv_l),
-                     pack_half2(f[6] * inv_l, f[7] * inv_l));
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t orr[32];
+        tmem_ld_32x32b_x32(o_tmem + cc * 64 + h2 * 32, orr);
+        tmem_wait_ld();
+        const int sub0 = h2 * 4;
+        const uint32_t row_addr = stage_base + cc * BOX_BYTES + lane * 128;
+        const uint32_t xr = lane & 7;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float* f = reinterpret_cast<const float*>(orr + 8 * g);
+          st_shared_v4(row_addr + (((sub0 + g) ^ xr) << 4), pack_half2(f[0] * inv_l, f[1] * inv_l),
+                       pack_half2(f[2] * inv_l, f[3] * inv_l), pack_half2(f[4] * inv_l, f[5] * inv_l),
+                       pack_half2(f[6] * inv_l, f[7] * inv_l));
+        }
       }
     }
     fence_proxy_async_smem();
     __syncwarp();
     const int row0 = q0 + int(q) * 32;
     if (lane == 0 && row0 < N) {
-      for (int c = 0; c < nv; ++c) tma_store_3d(&tmO, stage_base + c * BOX_BYTES, col0 + c * CW, row0, bh);
+      for (int cc = int(half); cc < nv; cc += SPLIT) tma_store_3d(&tmO, stage_base + cc * BOX_BYTES, col0 + cc * CW, row0, bh);
       tma_store_commit();
       tma_store_wait_all<0>();
     }
@@ -391,10 +429,10 @@ int launch_ffpa_2cta(const void* Q, const void* K, const void* V, void* O, int64
 extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N,
                                   int64_t D, float scale, int variant, void* stream) {
   using namespace b200k;
-  if (D == 32 || D == 64 || D == 96 || D == 128)
+  if (D == 32 || D == 64 || D == 96 || (D == 128 && !(variant & 16)))  // variant bit 16: run D=128 on this kernel (experiment)
     return b200k_fa2_fwd_f16(Q, K, V, O, B, H, N, D, scale, 0, variant, stream);
   if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_ffpa_fwd_f16: null pointer");
-  if (D < 192 || D > 1024 || (D % 64) != 0)
+  if (D < 128 || D > 1024 || (D % 64) != 0)
     return set_error(B200K_EHEADDIM, "headdim not support! (b200k_ffpa_fwd_f16: D=%lld; supported 32/64/96/128 and 192..1024 step 64)",
                      (long long)D);
   if (B < 1 || H < 1 || N < 1 || N > INT32_MAX || B * H > 65535)
@@ -423,14 +461,21 @@ extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, v
   const int slices = int((D + 255) / 256);
   dim3 grid(unsigned((N + 127) / 128), unsigned(slices), unsigned(BH));
   const float scale_log2 = scale * 1.4426950408889634f;
-  if (q_resident) {
-    auto kern = ffpa_fwd_tcgen05_kernel<true>;
+  // two softmax warpgroups per row when the tile is exponent-bound (small D); variant bit 32 flips the choice
+  const bool split = ((D <= 256) ? 1 : 0) ^ ((variant & 32) ? 1 : 0);
+  const int serial = ((variant & 4) ? 1 : 0) | (((variant >> 6) & 3) << 1);  // bits 6,7: timing probes
+  if (q_resident && split) {
+    auto kern = ffpa_fwd_tcgen05_kernel<true, 2>;
     B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, ffpa::THREADS, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, (variant & 4) ? 1 : 0);
+    kern<<<grid, 384, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, serial);
+  } else if (q_resident) {
+    auto kern = ffpa_fwd_tcgen05_kernel<true, 1>;
+    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 256, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, serial);
   } else {
-    auto kern = ffpa_fwd_tcgen05_kernel<false>;
+    auto kern = ffpa_fwd_tcgen05_kernel<false, 1>;
     B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, ffpa::THREADS, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, (variant & 4) ? 1 : 0);
+    kern<<<grid, 256, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, serial);
   }
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;
