@@ -393,9 +393,13 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int e = 0; e < 8; ++e) x[e] = ffma2(make_float2(s[c0 + 2 * e], s[c0 + 2 * e + 1]), scale2, negm2);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          x[e].x = fast_exp2(x[e].x);
-          // every 4th exponential is evaluated on the FMA pipe (exp2_poly3) when requested
-          x[e].y = (POLY && (e & 1)) ? exp2_poly3(x[e].y) : fast_exp2(x[e].y);
+          // POLY: 3 of every 8 pairs (37.5 %) are evaluated on the FMA pipe with packed fp32x2 arithmetic
+          if (POLY && (e == 2 || e == 5 || e == 7)) {
+            x[e] = exp2_poly3_x2(x[e]);
+          } else {
+            x[e].x = fast_exp2(x[e].x);
+            x[e].y = fast_exp2(x[e].y);
+          }
         }
 #pragma unroll
         for (int e = 0; e < 8; e += 2) {
@@ -516,8 +520,8 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
   // Experiment switches (measurements in profiles/r01_fa2_variants.txt, B200, (4,48,8192,64)):
   //   0x200 exp2-phase turn-taking between the two softmax warpgroups: +4% before the packed-math rewrite of the
   //         softmax loop, -2% after it (758 vs 773 TFLOP/s) -> off by default;
-  //   0x800 25% of the exponentials as a degree-3 polynomial on the FMA pipe: 712 vs 773 TFLOP/s (the loop is
-  //         issue-bound, not MUFU-bound) -> off by default.
+  //   0x800 part of the exponentials as a degree-3 polynomial on the FMA pipe (FA-4 style): 25 % scalar 712, 37.5 %
+  //         packed fp32x2 691 vs 773 TFLOP/s without -> off by default.
   const int pingpong = (variant & 0x200) ? 1 : 0;
   const bool poly = (variant & 0x800) != 0;
   if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_fa2_fwd_f16: null pointer");

@@ -403,4 +403,19 @@ __device__ __forceinline__ float exp2_poly3(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// Packed (fp32x2) version of exp2_poly3: two exponentials per instruction slot on the FMA pipe.
+__device__ __forceinline__ float2 exp2_poly3_x2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), neg_magic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 t = fadd2(x, magic);
+  const float2 nf = fadd2(t, neg_magic);
+  const float2 f = fadd2(x, make_float2(-nf.x, -nf.y));
+  float2 p = ffma2(f, make_float2(5.500892858e-02f, 5.500892858e-02f), make_float2(2.422109601e-01f, 2.422109601e-01f));
+  p = ffma2(p, f, make_float2(6.932829276e-01f, 6.932829276e-01f));
+  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
 }  // namespace b200k
