@@ -139,38 +139,38 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   if (warp == 0) {
     // ---------------------------------------------------------------------------------- TMA producer
-    // (whole warp convergent, one elected lane issues: keeps addresses / coordinates on the uniform datapath)
-    {
+    // One lane is elected ONCE and runs the whole producer loop alone (waits included): per-batch elect + __syncwarp
+    // and 32-lane barrier polling cost ~35 % of the tile time in tools/ubench/ubench_attn.cu; electing through
+    // elect.sync (not `lane == 0`) keeps operands on the uniform datapath (no R2UR waterfall loops).
+    if (elect_one()) {
       auto load_q = [&](int i) {
         const uint32_t bar = bar_q_full + 8 * i;
-        if (elect_one()) {
+        {
           mbar_arrive_expect_tx(bar, Cfg::Q_TILE_BYTES);
 #pragma unroll
           for (int c = 0; c < NCH; ++c)
             tma_load_3d(smem_q + i * Cfg::Q_TILE_BYTES + c * Cfg::Q_CHUNK_BYTES, &tmQ, bar, c * CW, q0 + i * 128, bh,
                         kPolicyEvictFirst);
         }
-        __syncwarp();
       };
       auto load_k = [&](int j) {
         const int s = j % STAGES;
         mbar_wait(bar_k_empty + 8 * s, ((j / STAGES) & 1) ^ 1);
         const uint32_t bar = bar_k_full + 8 * s;
-        if (elect_one()) {
+        {
           mbar_arrive_expect_tx(bar, Cfg::KV_TILE_BYTES);
 #pragma unroll
           for (int c = 0; c < NCH; ++c)
             tma_load_3d(smem_k + s * Cfg::KV_TILE_BYTES + c * Cfg::KV_CHUNK_BYTES, &tmK, bar, c * CW, j * BC, bh,
                         kPolicyEvictLast);
         }
-        __syncwarp();
       };
       auto load_v = [&](int j) {
         const int s = j % STAGES;
         mbar_wait(bar_v_empty + 8 * s, ((j / STAGES) & 1) ^ 1);
         const uint32_t bar = bar_v_full + 8 * s;
         const uint32_t dst = smem_v + s * Cfg::KV_TILE_BYTES;
-        if (elect_one()) {
+        {
           mbar_arrive_expect_tx(bar, Cfg::KV_TILE_BYTES);
           if constexpr (Cfg::V_DN) {
             // V^T tile: D rows x BC keys, as [D rows x 64 keys] 128B-swizzled boxes (keys contiguous = K-major B operand)
@@ -183,7 +183,6 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
               tma_load_3d(dst + c * Cfg::KV_CHUNK_BYTES, &tmV, bar, c * CW, j * BC, bh, kPolicyEvictLast);
           }
         }
-        __syncwarp();
       };
       load_q(0);
       load_k(0);
@@ -195,9 +194,8 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------------- MMA issuer
-    // The whole warp runs this loop convergently (waits, address arithmetic: warp-uniform, uniform datapath); the
-    // tcgen05.mma / commit instructions themselves are issued by one elected lane.
-    {
+    // One lane is elected once and runs the whole issue loop (see the producer above).
+    if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(128, BC, true, false, false);  // Q, K both K-major (D contiguous)
       // P from TMEM; V is MN-major ([keys, D], D contiguous) or, for V^T input, K-major ([D, keys], keys contiguous)
       constexpr uint32_t idesc_o = make_idesc_f16(128, D, true, false, !Cfg::V_DN);
@@ -211,7 +209,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const uint32_t q_addr = smem_q + i * Cfg::Q_TILE_BYTES;
         const uint32_t k_addr = smem_k + stage * Cfg::KV_TILE_BYTES;
         const uint32_t d_tmem = tmem_base + (i ? Cfg::S_COL1 : Cfg::S_COL0);
-        if (elect_one()) {
+        {
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
             const uint32_t q_off = (k / KSTEPS_PER_CHUNK) * Cfg::Q_CHUNK_BYTES + (k % KSTEPS_PER_CHUNK) * 32;
@@ -221,13 +219,12 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           umma_commit(bar_a);
           if (bar_b) umma_commit(bar_b);
         }
-        __syncwarp();
       };
       auto issue_pv = [&](int i, int stage, bool accumulate, uint32_t bar_a, uint32_t bar_b, uint32_t bar_c) {
         const uint32_t v_addr = smem_v + stage * Cfg::KV_TILE_BYTES;
         const uint32_t d_tmem = tmem_base + (i ? Cfg::O_COL1 : Cfg::O_COL0);
         const uint32_t p_tmem = tmem_base + (i ? Cfg::P_COL1 : Cfg::P_COL0);
-        if (elect_one()) {
+        {
 #pragma unroll
           for (int k = 0; k < BC / 16; ++k) {
             // 16 keys = 8 packed fp16x2 columns of P; 16 rows of V = 16 * ROWB bytes (V^T: 32 bytes inside a 64-key box)
@@ -239,7 +236,6 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           if (bar_b) umma_commit(bar_b);
           if (bar_c) umma_commit(bar_c);
         }
-        __syncwarp();
       };
 
       mbar_wait(bar_q_full, 0);
@@ -275,14 +271,14 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           // scores of the next KV tile: only needs the S columns back (the softmax warps hold tile j in registers)
           const int s1 = (j + 1) % STAGES;
           mbar_wait(bar_k_full + 8 * s1, ((j + 1) / STAGES) & 1);
-          if (lane == 0) tr(0, j, 0);
+          tr(0, j, 0);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             mbar_wait(bar_s_free + 8 * i, j & 1);
-            if (lane == 0) tr(0, j, 1 + 2 * i);
+            tr(0, j, 1 + 2 * i);
             tc_fence_after();
             issue_s(i, s1, bar_s_full + 8 * i, i == 1 ? bar_k_empty + 8 * s1 : 0u);
-            if (lane == 0) tr(0, j, 2 + 2 * i);
+            tr(0, j, 2 + 2 * i);
           }
         }
         const int s = j % STAGES;
@@ -290,12 +286,12 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           mbar_wait(bar_p_full + 8 * i, j & 1);
-          if (lane == 0) tr(0, j, 5 + i);
+          tr(0, j, 5 + i);
           tc_fence_after();
           issue_pv(i, s, j > 0, bar_p_free + 8 * i, (j == T - 1) ? bar_o_full + 8 * i : 0u,
                    i == 1 ? bar_v_empty + 8 * s : 0u);
         }
-        if (lane == 0) tr(0, j, 7);
+        tr(0, j, 7);
       }
     }
   } else if (warp >= 4) {

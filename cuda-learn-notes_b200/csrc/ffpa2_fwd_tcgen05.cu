@@ -58,7 +58,7 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);  // warp-uniform for the compiler
   const bool leader = (rank == 0);
   const int bh = blockIdx.z;
   const int q0 = blockIdx.x * BR;             // grid.x is even: CTA pair = Q tiles (2c, 2c+1)
@@ -95,18 +95,19 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   if (warp == 0) {
     // ---------------------------------------------------------------------------------- TMA producer (both CTAs)
+    // one lane is elected once and runs the whole role loop alone (see fa2_fwd_tcgen05.cu / tools/ubench/ubench_attn.cu)
+    if (elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
     auto advance = [&]() {
       if (++stage == stages) { stage = 0; phase ^= 1; }
     };
     if (Q_RESIDENT) {
-      if (elect_one()) {
+      {
         if (leader) mbar_arrive_expect_tx(bar_q_full, 2 * nqk * QBOX);
         const uint32_t qb = mapa(bar_q_full, 0);
         for (int c = 0; c < nqk; ++c) tma_load_3d_2sm(smem_q + c * QBOX, &tmQ, qb, c * CW, q0, bh, kPolicyEvictFirst);
       }
-      __syncwarp();
     }
     auto load_qk = [&](int j) {
       if (Q_RESIDENT) {
@@ -114,26 +115,24 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const int nb = min(4, nqk - c);
           const uint32_t dst = smem_ring + stage * STAGE_BYTES;
-          if (elect_one()) {
+          {
             if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * nb * KBOX);
             const uint32_t fb = mapa(bar_full + 8 * stage, 0);
             for (int b = 0; b < nb; ++b)
               tma_load_3d_2sm(dst + b * KBOX, &tmKh, fb, (c + b) * CW, j * BC + int(rank) * 64, bh, kPolicyEvictLast);
           }
-          __syncwarp();
           advance();
         }
       } else {
         for (int c = 0; c < nqk; ++c) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t dst = smem_ring + stage * STAGE_BYTES;
-          if (elect_one()) {
+          {
             if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * (QBOX + KBOX));
             const uint32_t fb = mapa(bar_full + 8 * stage, 0);
             tma_load_3d_2sm(dst, &tmQ, fb, c * CW, q0, bh, kPolicyEvictLast);
             tma_load_3d_2sm(dst + QBOX, &tmKh, fb, c * CW, j * BC + int(rank) * 64, bh, kPolicyEvictLast);
           }
-          __syncwarp();
           advance();
         }
       }
@@ -141,13 +140,12 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     auto load_v = [&](int j) {
       mbar_wait(bar_empty + 8 * stage, phase ^ 1);
       const uint32_t dst = smem_ring + stage * STAGE_BYTES;
-      if (elect_one()) {
+      {
         if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * 2 * VBOX);
         const uint32_t fb = mapa(bar_full + 8 * stage, 0);
         tma_load_3d_2sm(dst, &tmV, fb, my_col0, j * BC, bh, kPolicyEvictLast);
         tma_load_3d_2sm(dst + VBOX, &tmV, fb, my_col0 + CW, j * BC, bh, kPolicyEvictLast);
       }
-      __syncwarp();
       advance();
     };
     load_qk(0);
@@ -155,9 +153,11 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (j + 1 < T) load_qk(j + 1);
       load_v(j);
     }
+    }
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------------- MMA issuer (leader CTA)
-    if (leader) {
+    // one lane is elected once and runs the whole role loop alone (see fa2_fwd_tcgen05.cu / tools/ubench/ubench_attn.cu)
+    if (elect_one() && leader) {  // this order keeps the MMA issue free of waterfall loops (SASS-checked)
       constexpr uint32_t idesc_s = make_idesc_f16(256, BC, true, false, false);   // M = 256 over the CTA pair
       constexpr uint32_t idesc_o = make_idesc_f16(256, 256, true, false, true);   // N = 256: 128 columns per CTA
       constexpr uint64_t qk_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);
@@ -175,7 +175,7 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tc_fence_after();
             const uint32_t kb = smem_ring + stage * STAGE_BYTES;
             const int nb = min(4, nqk - c);
-            if (elect_one()) {
+            {
               for (int b = 0; b < nb; ++b) {
                 const uint32_t qa = smem_q + (c + b) * QBOX;
 #pragma unroll
@@ -186,7 +186,6 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
               umma_commit_2sm(bar_empty + 8 * stage, 0b11);
               if (c + 4 >= nqk) umma_commit_2sm(bar_s_full + 8 * buf, 0b11);
             }
-            __syncwarp();
             advance();
           }
         } else {
@@ -195,7 +194,7 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tc_fence_after();
             const uint32_t qa = smem_ring + stage * STAGE_BYTES;
             const uint32_t kb = qa + QBOX;
-            if (elect_one()) {
+            {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_ss<2>(d_tmem, smem_desc(qk_hi, qa + k * 32), smem_desc(qk_hi, kb + k * 32), idesc_s,
@@ -203,7 +202,6 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
               umma_commit_2sm(bar_empty + 8 * stage, 0b11);
               if (c + 1 >= nqk) umma_commit_2sm(bar_s_full + 8 * buf, 0b11);
             }
-            __syncwarp();
             advance();
           }
         }
@@ -213,7 +211,7 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         const uint32_t va = smem_ring + stage * STAGE_BYTES;
-        if (elect_one()) {
+        {
 #pragma unroll
           for (int k = 0; k < BC / 16; ++k)
             umma_ts<2>(tmem_base + O_COL, p_tmem + k * 8, smem_desc(v_hi, va + k * 16 * 128), idesc_o,
@@ -222,7 +220,6 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           umma_commit_2sm(bar_pv_done, 0b11);
           if (last_tile) umma_commit_2sm(bar_o_full, 0b11);
         }
-        __syncwarp();
         advance();
       };
       if (Q_RESIDENT) {

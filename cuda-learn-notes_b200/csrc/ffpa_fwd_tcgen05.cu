@@ -105,20 +105,19 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   if (warp == 0) {
     // ---------------------------------------------------------------------------------- TMA producer
-    // (whole warp convergent; one elected lane issues expect_tx + TMA)
-    {
+    // one lane is elected once and runs the whole role loop alone (see fa2_fwd_tcgen05.cu / tools/ubench/ubench_attn.cu)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() {
         if (++stage == stages) { stage = 0; phase ^= 1; }
       };
       if (Q_RESIDENT) {
-        if (elect_one()) {
+        {
           mbar_arrive_expect_tx(bar_q_full, nqk * BOX_BYTES);
           for (int c = 0; c < nqk; ++c)
             tma_load_3d(smem_q + c * BOX_BYTES, &tmQ, bar_q_full, c * CW, q0, bh, kPolicyEvictFirst);
         }
-        __syncwarp();
       }
       auto load_qk = [&](int j) {
         if (Q_RESIDENT) {
@@ -126,24 +125,22 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             const int nb = min(2, nqk - c);
             const uint32_t dst = smem_ring + stage * STAGE_BYTES;
-            if (elect_one()) {
+            {
               mbar_arrive_expect_tx(bar_full + 8 * stage, nb * BOX_BYTES);
               for (int b = 0; b < nb; ++b)
                 tma_load_3d(dst + b * BOX_BYTES, &tmK, bar_full + 8 * stage, (c + b) * CW, j * BC, bh, kPolicyEvictLast);
             }
-            __syncwarp();
             advance();
           }
         } else {
           for (int c = 0; c < nqk; ++c) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             const uint32_t dst = smem_ring + stage * STAGE_BYTES;
-            if (elect_one()) {
+            {
               mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * BOX_BYTES);
               tma_load_3d(dst, &tmQ, bar_full + 8 * stage, c * CW, q0, bh, kPolicyEvictLast);
               tma_load_3d(dst + BOX_BYTES, &tmK, bar_full + 8 * stage, c * CW, j * BC, bh, kPolicyEvictLast);
             }
-            __syncwarp();
             advance();
           }
         }
@@ -153,12 +150,11 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const int nb = min(2, nv - c);
           const uint32_t dst = smem_ring + stage * STAGE_BYTES;
-          if (elect_one()) {
+          {
             mbar_arrive_expect_tx(bar_full + 8 * stage, nb * BOX_BYTES);
             for (int b = 0; b < nb; ++b)
               tma_load_3d(dst + b * BOX_BYTES, &tmV, bar_full + 8 * stage, col0 + (c + b) * CW, j * BC, bh, kPolicyEvictLast);
           }
-          __syncwarp();
           advance();
         }
       };
@@ -171,8 +167,8 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------------- MMA issuer
-    // (whole warp convergent; tcgen05.mma / commit issued by one elected lane)
-    {
+    // one lane is elected once and runs the whole role loop alone (see fa2_fwd_tcgen05.cu / tools/ubench/ubench_attn.cu)
+    if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(128, BC, true, false, false);
       constexpr uint64_t qk_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);
       constexpr uint64_t v_hi = make_smem_desc_hi(BOX_BYTES, 1024, kSwizzle128B);
@@ -189,7 +185,7 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             tc_fence_after();
             const uint32_t kb = smem_ring + stage * STAGE_BYTES;
             const int nb = min(2, nqk - c);
-            if (elect_one()) {
+            {
               for (int b = 0; b < nb; ++b) {
                 const uint32_t qa = smem_q + (c + b) * BOX_BYTES;
 #pragma unroll
@@ -200,7 +196,6 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               umma_commit(bar_empty + 8 * stage);
               if (c + 2 >= nqk) umma_commit(bar_s_full + 8 * buf);
             }
-            __syncwarp();
             advance();
           }
         } else {
@@ -209,7 +204,7 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             tc_fence_after();
             const uint32_t qa = smem_ring + stage * STAGE_BYTES;
             const uint32_t kb = qa + BOX_BYTES;
-            if (elect_one()) {
+            {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_ss<1>(d_tmem, smem_desc(qk_hi, qa + k * 32), smem_desc(qk_hi, kb + k * 32), idesc_s,
@@ -217,7 +212,6 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               umma_commit(bar_empty + 8 * stage);
               if (c + 1 >= nqk) umma_commit(bar_s_full + 8 * buf);
             }
-            __syncwarp();
             advance();
           }
         }
@@ -231,7 +225,7 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           const uint32_t va = smem_ring + stage * STAGE_BYTES;
           const uint32_t idesc_o = make_idesc_f16(128, uint32_t(nb * CW), true, false, true);
           const uint32_t d_tmem = tmem_base + O_COL + c * CW;
-          if (elect_one()) {
+          {
 #pragma unroll
             for (int k = 0; k < BC / 16; ++k)
               umma_ts<1>(d_tmem, p_tmem + k * 8, smem_desc(v_hi, va + k * 16 * 128), idesc_o,
@@ -242,7 +236,6 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               if (last_tile) umma_commit(bar_o_full);
             }
           }
-          __syncwarp();
           advance();
         }
       };
