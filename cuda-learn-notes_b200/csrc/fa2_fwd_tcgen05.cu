@@ -20,6 +20,9 @@
 // reference where it matters: scores scaled by 1/sqrt(D), softmax statistics in fp32, P rounded to fp16 before PV
 // (share_qkv.cu:L431-478); the MMA accumulators are fp32 here (the reference default is fp16 accumulate).
 #include <cmath>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "abi_common.cuh"
 #include "ptx.cuh"
@@ -66,7 +69,7 @@ constexpr float kRescaleThreshold = 8.0f;
 constexpr int kTraceIters = 32, kTraceEvents = 8;
 static unsigned long long* g_fa2_trace = nullptr;  // set through b200k_debug_set_trace()
 
-template <class Cfg, bool TRACE, bool POLY>
+template <class Cfg, bool TRACE, int POLY, int NP>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int N,
@@ -91,8 +94,8 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t bar_v_empty = bar_v_full + 8 * STAGES;   // STAGES
   const uint32_t bar_s_full = bar_v_empty + 8 * STAGES;   // 2   S_i(j) ready                 (MMA -> softmax i)
   const uint32_t bar_s_free = bar_s_full + 16;            // 2   S_i(j) is in registers       (softmax i -> MMA)
-  const uint32_t bar_p_full = bar_s_free + 16;            // 2   P_i(j) written, O_i rescaled (softmax i -> MMA)
-  const uint32_t bar_p_free = bar_p_full + 16;            // 2   PV_i(j) done: P_i free, O_i stable (MMA -> softmax i)
+  const uint32_t bar_p_full = bar_s_free + 16;            // 2x4 piece p of P_i(j) written (and O_i rescaled) (softmax i -> MMA)
+  const uint32_t bar_p_free = bar_p_full + 64;            // 2   PV_i(j) done: P_i free, O_i stable (MMA -> softmax i)
   const uint32_t bar_o_full = bar_p_free + 16;            // 2   last PV_i done               (MMA -> softmax i)
   const uint32_t tmem_slot = bar_o_full + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
@@ -116,7 +119,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_init(bar_q_full + 8 * i, 1);
       mbar_init(bar_s_full + 8 * i, 1);
       mbar_init(bar_s_free + 8 * i, 4);
-      mbar_init(bar_p_full + 8 * i, 4);
+      for (int p = 0; p < 4; ++p) mbar_init(bar_p_full + 32 * i + 8 * p, 4);
       mbar_init(bar_p_free + 8 * i, 1);
       mbar_init(bar_o_full + 8 * i, 1);
     }
@@ -220,13 +223,21 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           if (bar_b) umma_commit(bar_b);
         }
       };
-      auto issue_pv = [&](int i, int stage, bool accumulate, uint32_t bar_a, uint32_t bar_b, uint32_t bar_c) {
+      // O_i += P_i V.  P arrives in NP pieces of BC/NP keys (the softmax warps hand each piece over as soon as it is
+      // written), so the first MMAs of PV_i(j) run under the exponentials of the later pieces.
+      auto issue_pv = [&](int i, int stage, int j, uint32_t bar_a, uint32_t bar_b, uint32_t bar_c) {
         const uint32_t v_addr = smem_v + stage * Cfg::KV_TILE_BYTES;
         const uint32_t d_tmem = tmem_base + (i ? Cfg::O_COL1 : Cfg::O_COL0);
         const uint32_t p_tmem = tmem_base + (i ? Cfg::P_COL1 : Cfg::P_COL0);
+        const bool accumulate = j > 0;
         {
 #pragma unroll
           for (int k = 0; k < BC / 16; ++k) {
+            if (k % (BC / 16 / NP) == 0) {
+              mbar_wait(bar_p_full + 32 * i + 8 * (k / (BC / 16 / NP)), j & 1);
+              tc_fence_after();
+              if (k == 0) tr(0, j, 5 + i);
+            }
             // 16 keys = 8 packed fp16x2 columns of P; 16 rows of V = 16 * ROWB bytes (V^T: 32 bytes inside a 64-key box)
             const uint32_t v_off = Cfg::V_DN ? uint32_t((k / 4) * (D * 128) + (k % 4) * 32) : uint32_t(k * 16 * ROWB);
             umma_ts<1>(d_tmem, p_tmem + k * 8, smem_desc(v_hi, v_addr + v_off), idesc_o,
@@ -251,18 +262,19 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const int s = j % STAGES;
           const int s1 = (j + 1) % STAGES;
           mbar_wait(bar_v_full + 8 * s, (j / STAGES) & 1);
+          tr(0, j, 0);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            mbar_wait(bar_p_full + 8 * i, j & 1);
-            tc_fence_after();
-            issue_pv(i, s, j > 0, bar_p_free + 8 * i, (j == T - 1) ? bar_o_full + 8 * i : 0u,
+            issue_pv(i, s, j, bar_p_free + 8 * i, (j == T - 1) ? bar_o_full + 8 * i : 0u,
                      i == 1 ? bar_v_empty + 8 * s : 0u);
+            tr(0, j, 1 + 2 * i);
             if (j + 1 < T) {
               if (i == 0) {
                 mbar_wait(bar_k_full + 8 * s1, ((j + 1) / STAGES) & 1);
                 tc_fence_after();
               }
               issue_s(i, s1, bar_s_full + 8 * i, i == 1 ? bar_k_empty + 8 * s1 : 0u);
+              tr(0, j, 2 + 2 * i);
             }
           }
           continue;
@@ -285,10 +297,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mbar_wait(bar_v_full + 8 * s, (j / STAGES) & 1);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          mbar_wait(bar_p_full + 8 * i, j & 1);
-          tr(0, j, 5 + i);
-          tc_fence_after();
-          issue_pv(i, s, j > 0, bar_p_free + 8 * i, (j == T - 1) ? bar_o_full + 8 * i : 0u,
+          issue_pv(i, s, j, bar_p_free + 8 * i, (j == T - 1) ? bar_o_full + 8 * i : 0u,
                    i == 1 ? bar_v_empty + 8 * s : 0u);
         }
         tr(0, j, 7);
@@ -334,15 +343,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int c = 0; c < BC; ++c)
           if (c >= valid) s[c] = -INFINITY;
       }
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
-#pragma unroll
-      for (int c = 4; c < BC; c += 4) {
-        mx0 = fmaxf(mx0, s[c]);
-        mx1 = fmaxf(mx1, s[c + 1]);
-        mx2 = fmaxf(mx2, s[c + 2]);
-        mx3 = fmaxf(mx3, s[c + 3]);
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      const float mx = row_max<BC>(s) * scale_log2;
       // Has PV_i(j-1) been observed complete (O_i stable, P_i columns free)?  With ALIAS_P it always has: S_i(j) was
       // issued after PV_i(j-1) and tcgen05.commit covers all prior MMAs, so s_full(j) already implies it.
       bool pv_done = (j == 0) || Cfg::ALIAS_P;
@@ -382,6 +383,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       float neg_m = -m_ref;
       if (pingpong) asm volatile("" : "+f"(neg_m));  // pins the exponentials behind the turn-taking barrier
       const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(neg_m, neg_m);
+      constexpr int PIECE = BC / NP;  // keys per piece of P
 #pragma unroll
       for (int c0 = 0; c0 < BC; c0 += 16) {
         float2 x[8];
@@ -389,8 +391,10 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int e = 0; e < 8; ++e) x[e] = ffma2(make_float2(s[c0 + 2 * e], s[c0 + 2 * e + 1]), scale2, negm2);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          // POLY: 3 of every 8 pairs (37.5 %) are evaluated on the FMA pipe with packed fp32x2 arithmetic
-          if (POLY && (e == 2 || e == 5 || e == 7)) {
+          // POLY of every 8 pairs are evaluated on the FMA/ALU pipes with packed fp32x2 arithmetic (no MUFU)
+          const bool on_fma = (POLY == 1 && e == 3) || (POLY == 2 && (e == 2 || e == 6)) ||
+                                  (POLY == 3 && (e == 2 || e == 5 || e == 7)) || (POLY == 4 && (e & 1));
+          if (on_fma) {
             x[e] = exp2_poly3_x2(x[e]);
           } else {
             x[e].x = fast_exp2(x[e].x);
@@ -404,22 +408,24 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           sr[(c0 >> 1) + e] = pack_half2(x[e].x, x[e].y);
           sr[(c0 >> 1) + e + 1] = pack_half2(x[e + 1].x, x[e + 1].y);
         }
+        if ((c0 + 16) % PIECE == 0) {
+          // piece complete: hand it to the MMA thread now, PV of this piece runs under the next piece's exponentials
+          const int pc = c0 / PIECE;
+          if (pc == 0 && !pv_done) {  // P_i(j-1) must have been consumed before it is overwritten (long since true)
+            mbar_wait(bar_p_free + 8 * i, (j - 1) & 1);
+            tc_fence_after();
+          }
+          if (tw && pc == 0) tr(1 + i, j, 3);
+          tmem_st_n<PIECE / 2>(p_tmem + pc * (PIECE / 2), sr + pc * (PIECE / 2));
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_p_full + 32 * i + 8 * pc);
+          if (tw && pc == 0) tr(1 + i, j, 4);
+        }
       }
       l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
       if (pingpong) named_bar_arrive(2 - i, 256);
-      if (tw) tr(1 + i, j, 3);
-      if (!pv_done) {  // P_i(j-1) must have been consumed before it is overwritten (normally long since true)
-        mbar_wait(bar_p_free + 8 * i, (j - 1) & 1);
-        tc_fence_after();
-      }
-      if (tw) tr(1 + i, j, 4);
-#pragma unroll
-      for (int c = 0; c < BC / 64; ++c) tmem_st_32x32b_x32(p_tmem + c * 32, sr + c * 32);
-      tmem_wait_st();
-      if (tw) tr(1 + i, j, 5);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p_full + 8 * i);
       if (tw) tr(1 + i, j, 6);
     }
     // ---- epilogue: O_i / l -> fp16 -> swizzled smem (reusing this tile's Q buffer) -> TMA store
@@ -461,9 +467,13 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 2) tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
 }
 
+// P is handed to the MMA thread in this many pieces per KV tile (variant bits 12-13 override: 1, 2 or 4).
+constexpr int kDefaultPieces = 2;
+
 template <class Cfg>
 static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N, float scale,
-                      cudaStream_t stream, const DeviceInfo& di, bool trace = false, int pingpong = 0, bool poly = false) {
+                      cudaStream_t stream, const DeviceInfo& di, int np = kDefaultPieces, bool trace = false, int pingpong = 0,
+                      int poly = 0) {
   constexpr int D = Cfg::D;
   const uint64_t BH = uint64_t(B) * uint64_t(H);
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -482,27 +492,36 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
   if ((rc = make_tmap_3d_u16(&tmO, O, BH, N, D, uint64_t(N) * D, D, 1, 32, Cfg::CW, Cfg::ROWB))) return rc;
   dim3 grid(unsigned((N + 255) / 256), unsigned(BH));
   const float scale_log2 = scale * 1.4426950408889634f;
-  if (poly && Cfg::D <= 64 && !Cfg::V_DN) {
-    auto kern = fa2_fwd_tcgen05_kernel<Cfg, false, (Cfg::D <= 64 && !Cfg::V_DN)>;
-    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, nullptr, pingpong);
-    B200K_CHECK_CUDA(cudaGetLastError());
-    return B200K_OK;
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, int, float,
+                        unsigned long long*, int);
+  Kern kern;
+  unsigned long long* tbuf = nullptr;
+  // Experiment / debug instantiations (piece counts, cycle trace, higher polynomial fractions) only exist for the two
+  // benchmark shapes; every configuration has the production pair (POLY 0 and 1, two pieces).
+  constexpr bool kLab = (Cfg::D == 64 || Cfg::D == 128) && !Cfg::V_DN && Cfg::BC == 128;
+  constexpr int P2 = kLab ? 2 : 1, P3 = kLab ? 3 : 1, P4 = kLab ? 4 : 1, NP1 = kLab ? 1 : kDefaultPieces,
+                NP4 = kLab ? 4 : kDefaultPieces;
+  constexpr bool TR = kLab;
+  if (trace && g_fa2_trace && kLab) {
+    tbuf = g_fa2_trace;
+    kern = poly ? fa2_fwd_tcgen05_kernel<Cfg, TR, 1, kDefaultPieces> : fa2_fwd_tcgen05_kernel<Cfg, TR, 0, kDefaultPieces>;
+  } else if (np != kDefaultPieces && kLab) {
+    kern = np == 1 ? fa2_fwd_tcgen05_kernel<Cfg, false, 0, NP1> : fa2_fwd_tcgen05_kernel<Cfg, false, 0, NP4>;
+  } else {
+    kern = poly == 0   ? fa2_fwd_tcgen05_kernel<Cfg, false, 0, kDefaultPieces>
+           : poly == 1 ? fa2_fwd_tcgen05_kernel<Cfg, false, 1, kDefaultPieces>
+           : poly == 2 ? fa2_fwd_tcgen05_kernel<Cfg, false, P2, kDefaultPieces>
+           : poly == 3 ? fa2_fwd_tcgen05_kernel<Cfg, false, P3, kDefaultPieces>
+                       : fa2_fwd_tcgen05_kernel<Cfg, false, P4, kDefaultPieces>;
   }
-  if (trace && g_fa2_trace) {
-    auto kern = fa2_fwd_tcgen05_kernel<Cfg, true, false>;
-    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, g_fa2_trace, pingpong);
-    B200K_CHECK_CUDA(cudaGetLastError());
-    return B200K_OK;
+  {  // the dynamic-smem attribute is per function and per device: set it once for each pair
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.insert({reinterpret_cast<const void*>(kern), di.device}).second)
+      B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   }
-  auto kern = fa2_fwd_tcgen05_kernel<Cfg, false, false>;
-  static bool attr_set[64] = {};
-  if (!attr_set[di.device]) {
-    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set[di.device] = true;
-  }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, nullptr, pingpong);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, tbuf, pingpong);
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;
 }
@@ -513,13 +532,20 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
                                  int64_t D, float scale, int v_is_dn, int variant, void* stream) {
   using namespace b200k;
   const bool trace = (variant & 0x100) != 0;  // debugging: cycle trace of CTA (0,0), see b200k_debug_set_trace
-  // Experiment switches (measurements in profiles/r01_fa2_variants.txt, B200, (4,48,8192,64)):
-  //   0x200 exp2-phase turn-taking between the two softmax warpgroups: +4% before the packed-math rewrite of the
-  //         softmax loop, -2% after it (758 vs 773 TFLOP/s) -> off by default;
-  //   0x800 part of the exponentials as a degree-3 polynomial on the FMA pipe (FA-4 style): 25 % scalar 712, 37.5 %
-  //         packed fp32x2 691 vs 773 TFLOP/s without -> off by default.
+  // Experiment switches (measurements in profiles/r01_fa2_variants.txt, B200, (4,48,8192,64) unless noted):
+  //   0x200        exp2-phase turn-taking between the two softmax warpgroups (named barriers): 744 vs 812 TFLOP/s
+  //                without -> off.  The cycle trace shows why: the MUFU pipe is the bottleneck either way and a turn
+  //                also holds the pipe through the P store / hand-over of the warpgroup that owns it.
+  //   bits 12-13   P handed to the MMA thread in 1 / 2 / 4 pieces per KV tile (1: 731, 2: 817, 4: 761) -> 2.
+  //   bits 14-16   n of every 8 exponential pairs evaluated as a degree-3 polynomial on the FMA/ALU pipes instead
+  //                of MUFU.EX2 (FlashAttention-4's trick): 0 -> 817, 1 -> 865, 2 -> 800, 3 -> 740, 4 -> 713;
+  //                D=128: 1100 / 1160 / 1140; D=32: 414 / 426; D=96: 912 / 920.  Default 1 (value 0), 7 = none.
+  //   0x800        older spelling of "3 of 8".
   const int pingpong = (variant & 0x200) ? 1 : 0;
-  const bool poly = (variant & 0x800) != 0;
+  const int poly_sel = (variant >> 14) & 7;
+  const int poly = poly_sel == 7 ? 0 : (poly_sel ? min(4, poly_sel) : ((variant & 0x800) ? 3 : 1));
+  const int np_sel = (variant >> 12) & 3;  // 0 default, 1 -> 1 piece, 2 -> 2 pieces, 3 -> 4 pieces
+  const int np = np_sel == 0 ? kDefaultPieces : (np_sel == 3 ? 4 : np_sel);
   if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_fa2_fwd_f16: null pointer");
   if (B < 1 || H < 1 || N < 1 || N > INT32_MAX || B * H > 65535)
     return set_error(B200K_ESHAPE, "b200k_fa2_fwd_f16: need B,H,N >= 1 and B*H <= 65535 (got B=%lld H=%lld N=%lld)",
@@ -534,19 +560,19 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (v_is_dn) {
     switch (D) {
-      case 32: return launch_fa2<Fa2Cfg<32, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
-      case 64: return launch_fa2<Fa2Cfg<64, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
-      case 96: return launch_fa2<Fa2Cfg<96, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di);
-      default: return launch_fa2<Fa2Cfg<128, 128, 2, true, true>>(Q, K, V, O, B, H, N, scale, s, di);
+      case 32: return launch_fa2<Fa2Cfg<32, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
+      case 64: return launch_fa2<Fa2Cfg<64, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
+      case 96: return launch_fa2<Fa2Cfg<96, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
+      default: return launch_fa2<Fa2Cfg<128, 128, 2, true, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
     }
   }
   switch (D) {
-    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, false, pingpong, poly);
-    case 64: return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong, poly);
-    case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di);
+    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
+    case 64: return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
+    case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
     default:
-      if (variant & 0x400) return launch_fa2<Fa2Cfg<128, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
-      return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, trace, pingpong);
+      if (variant & 0x400) return launch_fa2<Fa2Cfg<128, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
+      return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
   }
 }
 

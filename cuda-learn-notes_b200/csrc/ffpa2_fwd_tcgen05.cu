@@ -260,15 +260,7 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         for (int c = 0; c < 128; ++c)
           if (c >= valid) s[c] = -INFINITY;
       }
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
-#pragma unroll
-      for (int c = 4; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, s[c]);
-        mx1 = fmaxf(mx1, s[c + 1]);
-        mx2 = fmaxf(mx2, s[c + 2]);
-        mx3 = fmaxf(mx3, s[c + 3]);
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      const float mx = row_max<128>(s) * scale_log2;
       if (j == 0) {
         m_ref = mx;
       } else {

@@ -288,15 +288,7 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         for (int c = 0; c < COLS; ++c)
           if (c >= valid) s[c] = -INFINITY;
       }
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
-#pragma unroll
-      for (int c = 4; c < COLS; c += 4) {
-        mx0 = fmaxf(mx0, s[c]);
-        mx1 = fmaxf(mx1, s[c + 1]);
-        mx2 = fmaxf(mx2, s[c + 2]);
-        mx3 = fmaxf(mx3, s[c + 3]);
-      }
-      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = row_max<COLS>(s);
       if constexpr (SPLIT == 2) {
         // row max over both halves: both threads of a row end up with the identical value
         float* slot = xch + (j & 1) * 256;

@@ -108,6 +108,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// non-blocking probe (mbarrier.test_wait): has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
   printf("[b200k] mbarrier wait timed out: block (%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y,
          threadIdx.x, bar, parity);
@@ -407,15 +421,58 @@ __device__ __forceinline__ float exp2_poly3(float x) {
 __device__ __forceinline__ float2 exp2_poly3_x2(float2 x) {
   x.x = fmaxf(x.x, -126.0f);
   x.y = fmaxf(x.y, -126.0f);
-  const float2 magic = make_float2(12582912.0f, 12582912.0f), neg_magic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
   const float2 t = fadd2(x, magic);
-  const float2 nf = fadd2(t, neg_magic);
-  const float2 f = fadd2(x, make_float2(-nf.x, -nf.y));
+  const float2 nnf = ffma2(t, make_float2(-1.0f, -1.0f), magic);  // magic - t = -round(x), exact
+  const float2 f = fadd2(x, nnf);
   float2 p = ffma2(f, make_float2(5.500892858e-02f, 5.500892858e-02f), make_float2(2.422109601e-01f, 2.422109601e-01f));
   p = ffma2(p, f, make_float2(6.932829276e-01f, 6.932829276e-01f));
   p = ffma2(p, f, make_float2(1.0f, 1.0f));
-  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
-                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+  // exponent patch: bits(p) + (bits(t) << 23), one LEA per element on the ALU pipe
+  uint32_t rx, ry;
+  asm("{\n\t.reg .b32 u;\n\tshl.b32 u, %2, 23;\n\tadd.s32 %0, %1, u;\n\t}" : "=r"(rx) : "r"(__float_as_uint(p.x)), "r"(__float_as_uint(t.x)));
+  asm("{\n\t.reg .b32 u;\n\tshl.b32 u, %2, 23;\n\tadd.s32 %0, %1, u;\n\t}" : "=r"(ry) : "r"(__float_as_uint(p.y)), "r"(__float_as_uint(t.y)));
+  return make_float2(__uint_as_float(rx), __uint_as_float(ry));
+}
+
+// tcgen05.st of N consecutive 32-bit columns (N = 8, 16, 32 or 64) from registers r[0..N)
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r) {
+  static_assert(N == 8 || N == 16 || N == 32 || N == 64, "tmem_st_n");
+  if constexpr (N == 8) tmem_st_32x32b_x8(taddr, r);
+  if constexpr (N == 16) tmem_st_32x32b_x16(taddr, r);
+  if constexpr (N == 32) tmem_st_32x32b_x32(taddr, r);
+  if constexpr (N == 64) {
+    tmem_st_32x32b_x32(taddr, r);
+    tmem_st_32x32b_x32(taddr + 32, r + 32);
+  }
+}
+
+// 3-input max (FMNMX3): half the ALU-pipe slots of a 2-input max chain
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// max of s[0..N) with four independent FMNMX3 chains (N % 8 == 4 or N % 8 == 0, N >= 12)
+template <int N>
+__device__ __forceinline__ float row_max(const float* s) {
+  static_assert(N >= 12 && N % 4 == 0, "row_max");
+  float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
+  constexpr int FULL = 4 + ((N - 4) / 8) * 8;
+#pragma unroll
+  for (int c = 4; c < FULL; c += 8) {
+    m0 = fmax3(m0, s[c], s[c + 1]);
+    m1 = fmax3(m1, s[c + 2], s[c + 3]);
+    m2 = fmax3(m2, s[c + 4], s[c + 5]);
+    m3 = fmax3(m3, s[c + 6], s[c + 7]);
+  }
+  if constexpr (FULL < N) {
+    m0 = fmax3(m0, s[FULL], s[FULL + 1]);
+    m1 = fmax3(m1, s[FULL + 2], s[FULL + 3]);
+  }
+  return fmax3(m0, m1, fmaxf(m2, m3));
 }
 
 }  // namespace b200k

@@ -67,6 +67,24 @@ def test_large_logits_exercise_lazy_rescale():
     assert torch.allclose(_run(q, k, v).cpu().float(), oracle.attention(q, k, v).float(), **TOL)
 
 
+@pytest.mark.parametrize("variant", [0x1C000, 0x8000, 0x10000, 0x1000, 0x3000, 0x200])
+@pytest.mark.parametrize("D", [64, 128])
+def test_fa2_experiment_builds_agree_with_oracle(D, variant):
+    """Every selectable build of the FA-2 kernel (no / more polynomial exponentials, 1 / 4 P pieces, turn-taking)
+    must give the same answer as the default one; also covers very negative scores (masked-like keys) on the
+    polynomial exp2 path, which has to flush them to zero like MUFU.EX2 does."""
+    from b200k import ops
+
+    torch.manual_seed(D + variant)
+    B, H, N = 1, 2, 777
+    q, k, v = [torch.randn(B, H, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    k[:, :, 100:140] *= 24.0  # a band of keys with huge |scores|: exp2 arguments far below -126 for most rows
+    o = torch.full_like(q, float("nan"))
+    ops.fa2_fwd(q, k, v, o, variant=variant)
+    assert torch.isfinite(o).all()
+    assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), **TOL)
+
+
 def test_flash_attn_lib_and_ffpa_drop_in_entry_points():
     import ffpa_attn
     from b200k import flash_attn_lib
