@@ -9,11 +9,17 @@
 //   warps 8..11   softmax warpgroup for Q tile 1       (row max / exp2 / row sum in fp32 registers), P written as
 //                 fp16 into its OWN TMEM columns with tcgen05.st; O is rescaled in TMEM only when the row max grew
 //                 by more than 2^8 (lazy rescaling); the same threads normalise and store O at the end (TMA store).
-// TMEM columns:  S0 S1 (2 x BC fp32) | P0 P1 (2 x BC/2, packed fp16) | O0 O1 (2 x D fp32)   <= 512.
-// Because P does not alias S, the scores of KV tile j+1 are produced while the softmax warps still work on tile j:
-// the S columns are handed back right after the row has been read into registers (s_free), so a softmax
-// warpgroup never waits for the tensor core in steady state; PV of tile j overlaps softmax of tile j+1.
-// BC = 128 keys for D <= 64; BC = 64 for D = 96 / 128 so that the layout fits the 512 columns.
+// TMEM columns (512 per SM), BC = 128 keys per KV tile except D = 96 (BC = 64):
+//   D <= 96:  S0 S1 (2 x BC fp32) | P0 P1 (2 x BC/2, packed fp16) | O0 O1 (2 x D fp32).  P does not alias S, so the
+//             scores of KV tile j+1 are produced while the softmax warps still work on tile j: the S columns are
+//             handed back right after the row has been read into registers (s_free).
+//   D = 128:  S (ONE buffer, BC fp32) | P0 P1 | O0 O1 = 128 + 128 + 256.  The two Q tiles take turns on the S buffer:
+//             S_1(j) is issued once tile 0's warps hold S_0(j) in registers, S_0(j+1) once tile 1's hold S_1(j).
+//             The next scores of a tile therefore never wait for its own PV (as they must when P aliases S), and
+//             the two tiles run half a period apart, so their exponentials rarely compete for the MUFU pipe.
+//             (+12 % over the S0 S1 O0 O1 / P-aliases-S layout, which is kept as variant 0x400.)
+// P is handed to the MMA thread in pieces (two per KV tile for D <= 96: PV of the first half runs under the
+// exponentials of the second; one for D = 128, where PV is off the critical chain).
 //
 // Replaces kernels/flash-attn/mma/basic/flash_attn_mma_share_qkv.cu:L45-709 (kernel) / L711-886 (launcher) and the
 // other flash_attn_mma_stages_* variants (same math, different Ampere smem strategies).  Numerics follow the
@@ -29,7 +35,7 @@
 
 namespace b200k {
 
-template <int D_, int BC_, int STAGES_, bool V_DN_ = false, bool ALIAS_P_ = false>
+template <int D_, int BC_, int STAGES_, bool V_DN_ = false, bool ALIAS_P_ = false, bool SHARE_S_ = false>
 struct Fa2Cfg {
   static constexpr int D = D_;
   static constexpr int BC = BC_;                       // keys per KV tile
@@ -37,6 +43,13 @@ struct Fa2Cfg {
   // ALIAS_P: P overwrites the first BC/2 columns of S (needed when S0 S1 O0 O1 already fill the 512 columns, i.e.
   // D = 128 with BC = 128).  S_i(j+1) can then only be issued after PV_i(j), as in-order tcgen05 execution protects P.
   static constexpr bool ALIAS_P = ALIAS_P_;
+  // SHARE_S: ONE S buffer used by both Q tiles in turn (S | P0 P1 | O0 O1 = BC + BC + 2 D columns: the other way to fit
+  // D = 128 with BC = 128).  S_0(j+1) only needs the buffer back from tile 1 (its warps have S_1(j) in registers) and
+  // NOT PV_0(j), so the chain  S -> softmax -> PV -> next S  of ALIAS_P is cut: the next scores are computed while the
+  // softmax of the current ones runs.  The two tiles then necessarily run half a period apart (ping-pong), which
+  // also keeps their exponentials from competing for the MUFU pipe.
+  static constexpr bool SHARE_S = SHARE_S_;
+  static_assert(!(ALIAS_P && SHARE_S), "pick one");
   static constexpr bool V_DN = V_DN_;  // V passed transposed as [B,H,D,N] (the reference's *_swizzle_qkv entry points)
   static constexpr int CW = (D % 64 == 0) ? 64 : 32;  // width of one smem chunk along D (elements)
   static constexpr int NCH = D / CW;
@@ -49,14 +62,15 @@ struct Fa2Cfg {
   static constexpr int KV_TILE_BYTES = NCH * KV_CHUNK_BYTES;  // = BC * D * 2 (also for the transposed-V layout)
   static constexpr int BAR_BYTES = 1024;
   static constexpr int SMEM_BYTES = 1024 + BAR_BYTES + 2 * Q_TILE_BYTES + 2 * STAGES * KV_TILE_BYTES;
-  static constexpr int S_COL0 = 0, S_COL1 = BC;
-  static constexpr int P_COL0 = ALIAS_P ? S_COL0 : 2 * BC, P_COL1 = ALIAS_P ? S_COL1 : 2 * BC + BC / 2;
-  static constexpr int O_COL0 = ALIAS_P ? 2 * BC : 3 * BC, O_COL1 = O_COL0 + D;
+  static constexpr int S_COL0 = 0, S_COL1 = SHARE_S ? 0 : BC;
+  static constexpr int NS = SHARE_S ? 1 : 2;           // S buffers
+  static constexpr int P_COL0 = ALIAS_P ? S_COL0 : NS * BC, P_COL1 = ALIAS_P ? S_COL1 : NS * BC + BC / 2;
+  static constexpr int O_COL0 = ALIAS_P ? 2 * BC : (NS + 1) * BC, O_COL1 = O_COL0 + D;
   static constexpr int TMEM_COLS = 512;
   static constexpr int THREADS = 384;
   static_assert(D % 32 == 0 && D >= 32 && D <= 128, "head dim");
   static_assert(BC == 64 || BC == 128, "keys per tile");
-  static_assert((ALIAS_P ? 2 : 3) * BC + 2 * D <= 512, "TMEM columns");
+  static_assert((ALIAS_P ? 2 : NS + 1) * BC + 2 * D <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 232448, "smem");
 };
 
@@ -255,6 +269,38 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       issue_s(0, 0, bar_s_full, 0);
       mbar_wait(bar_q_full + 8, 0);
       tc_fence_after();
+      if constexpr (Cfg::SHARE_S) {
+        // One S buffer, the two tiles half a period apart.  Issue order per KV tile j (each step waits only for what it
+        // needs, and in steady state the waits are satisfied in exactly this order):
+        //   S_1(j)     once tile 0's warps hold S_0(j) in registers            (s_free0)
+        //   PV_1(j-1)  as tile 1's P halves arrive                              (p_full1)
+        //   S_0(j+1)   once tile 1's warps hold S_1(j) in registers            (s_free1)
+        //   PV_0(j)    as tile 0's P halves arrive                              (p_full0)
+        for (int j = 0; j < T; ++j) {
+          const int s = j % STAGES, s1 = (j + 1) % STAGES, sp = (j + STAGES - 1) % STAGES;
+          mbar_wait(bar_s_free, j & 1);
+          tc_fence_after();
+          issue_s(1, s, bar_s_full + 8, bar_k_empty + 8 * s);  // second and last reader of K(j)
+          tr(0, j, 4);
+          if (j > 0) {
+            mbar_wait(bar_v_full + 8 * sp, ((j - 1) / STAGES) & 1);
+            issue_pv(1, sp, j - 1, bar_p_free + 8, 0u, bar_v_empty + 8 * sp);
+            tr(0, j, 3);
+          }
+          if (j + 1 < T) {
+            mbar_wait(bar_k_full + 8 * s1, ((j + 1) / STAGES) & 1);
+            mbar_wait(bar_s_free + 8, j & 1);
+            tc_fence_after();
+            issue_s(0, s1, bar_s_full, 0u);
+            tr(0, j, 2);
+          }
+          mbar_wait(bar_v_full + 8 * s, (j / STAGES) & 1);
+          issue_pv(0, s, j, bar_p_free, (j == T - 1) ? bar_o_full : 0u, 0u);
+          tr(0, j, 1);
+        }
+        const int sl = (T - 1) % STAGES;
+        issue_pv(1, sl, T - 1, bar_p_free + 8, bar_o_full + 8, bar_v_empty + 8 * sl);
+      } else {
       issue_s(1, 0, bar_s_full + 8, bar_k_empty);
       for (int j = 0; j < T; ++j) {
         if constexpr (Cfg::ALIAS_P) {
@@ -301,6 +347,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                    i == 1 ? bar_v_empty + 8 * s : 0u);
         }
         tr(0, j, 7);
+      }
       }
     }
   } else if (warp >= 4) {
@@ -467,12 +514,9 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 2) tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
 }
 
-// P is handed to the MMA thread in this many pieces per KV tile (variant bits 12-13 override: 1, 2 or 4).
-constexpr int kDefaultPieces = 2;
-
 template <class Cfg>
 static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N, float scale,
-                      cudaStream_t stream, const DeviceInfo& di, int np = kDefaultPieces, bool trace = false, int pingpong = 0,
+                      cudaStream_t stream, const DeviceInfo& di, int np = 0, bool trace = false, int pingpong = 0,
                       int poly = 0) {
   constexpr int D = Cfg::D;
   const uint64_t BH = uint64_t(B) * uint64_t(H);
@@ -499,20 +543,25 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
   // Experiment / debug instantiations (piece counts, cycle trace, higher polynomial fractions) only exist for the two
   // benchmark shapes; every configuration has the production pair (POLY 0 and 1, two pieces).
   constexpr bool kLab = (Cfg::D == 64 || Cfg::D == 128) && !Cfg::V_DN && Cfg::BC == 128;
-  constexpr int P2 = kLab ? 2 : 1, P3 = kLab ? 3 : 1, P4 = kLab ? 4 : 1, NP1 = kLab ? 1 : kDefaultPieces,
-                NP4 = kLab ? 4 : kDefaultPieces;
+  // Pieces per KV tile in which P is handed to the MMA thread.  With the shared S buffer PV is off the critical chain
+  // and one hand-over per tile is best (D = 128: 1 -> 1267, 2 -> 1209, 4 -> 1202 TFLOP/s); otherwise two.
+  constexpr int DEF_NP = Cfg::SHARE_S ? 1 : 2;
+  constexpr int P2 = kLab ? 2 : 1, P3 = kLab ? 3 : 1, P4 = kLab ? 4 : 1;
+  constexpr int NPA = kLab ? (DEF_NP == 1 ? 2 : 1) : DEF_NP, NPB = kLab ? 4 : DEF_NP;  // the two non-default counts
   constexpr bool TR = kLab;
+  if (np == 0) np = DEF_NP;
   if (trace && g_fa2_trace && kLab) {
     tbuf = g_fa2_trace;
-    kern = poly ? fa2_fwd_tcgen05_kernel<Cfg, TR, 1, kDefaultPieces> : fa2_fwd_tcgen05_kernel<Cfg, TR, 0, kDefaultPieces>;
-  } else if (np != kDefaultPieces && kLab) {
-    kern = np == 1 ? fa2_fwd_tcgen05_kernel<Cfg, false, 0, NP1> : fa2_fwd_tcgen05_kernel<Cfg, false, 0, NP4>;
+    kern = poly ? fa2_fwd_tcgen05_kernel<Cfg, TR, 1, DEF_NP> : fa2_fwd_tcgen05_kernel<Cfg, TR, 0, DEF_NP>;
+  } else if (np != DEF_NP && kLab) {
+    kern = np == 4 ? (poly ? fa2_fwd_tcgen05_kernel<Cfg, false, 1, NPB> : fa2_fwd_tcgen05_kernel<Cfg, false, 0, NPB>)
+                   : (poly ? fa2_fwd_tcgen05_kernel<Cfg, false, 1, NPA> : fa2_fwd_tcgen05_kernel<Cfg, false, 0, NPA>);
   } else {
-    kern = poly == 0   ? fa2_fwd_tcgen05_kernel<Cfg, false, 0, kDefaultPieces>
-           : poly == 1 ? fa2_fwd_tcgen05_kernel<Cfg, false, 1, kDefaultPieces>
-           : poly == 2 ? fa2_fwd_tcgen05_kernel<Cfg, false, P2, kDefaultPieces>
-           : poly == 3 ? fa2_fwd_tcgen05_kernel<Cfg, false, P3, kDefaultPieces>
-                       : fa2_fwd_tcgen05_kernel<Cfg, false, P4, kDefaultPieces>;
+    kern = poly == 0   ? fa2_fwd_tcgen05_kernel<Cfg, false, 0, DEF_NP>
+           : poly == 1 ? fa2_fwd_tcgen05_kernel<Cfg, false, 1, DEF_NP>
+           : poly == 2 ? fa2_fwd_tcgen05_kernel<Cfg, false, P2, DEF_NP>
+           : poly == 3 ? fa2_fwd_tcgen05_kernel<Cfg, false, P3, DEF_NP>
+                       : fa2_fwd_tcgen05_kernel<Cfg, false, P4, DEF_NP>;
   }
   {  // the dynamic-smem attribute is per function and per device: set it once for each pair
     static std::mutex mu;
@@ -532,20 +581,26 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
                                  int64_t D, float scale, int v_is_dn, int variant, void* stream) {
   using namespace b200k;
   const bool trace = (variant & 0x100) != 0;  // debugging: cycle trace of CTA (0,0), see b200k_debug_set_trace
-  // Experiment switches (measurements in profiles/r01_fa2_variants.txt, B200, (4,48,8192,64) unless noted):
-  //   0x200        exp2-phase turn-taking between the two softmax warpgroups (named barriers): 744 vs 812 TFLOP/s
-  //                without -> off.  The cycle trace shows why: the MUFU pipe is the bottleneck either way and a turn
-  //                also holds the pipe through the P store / hand-over of the warpgroup that owns it.
-  //   bits 12-13   P handed to the MMA thread in 1 / 2 / 4 pieces per KV tile (1: 731, 2: 817, 4: 761) -> 2.
+  // Experiment switches (round-robin measurements on one B200, profiles/r01_fa2_variants.txt and r01_fa2_*.log;
+  // TFLOP/s at (4,48,8192,64) unless noted):
+  //   0x200        exp2-phase turn-taking between the two softmax warpgroups (named barriers): 744 vs 812 without ->
+  //                off.  A turn also holds the MUFU pipe through the P store / hand-over of the warpgroup that owns it.
+  //   0x400        D = 128 only: P aliases S (S0 S1 O0 O1) instead of the shared S buffer: 1122 vs 1223.
+  //   bits 12-13   P handed to the MMA thread in 1 / 2 / 4 pieces per KV tile.  D = 64: 731 / 817 / 761 -> 2;
+  //                D = 128 (shared S): 1267 / 1209 / 1202 -> 1.
   //   bits 14-16   n of every 8 exponential pairs evaluated as a degree-3 polynomial on the FMA/ALU pipes instead
   //                of MUFU.EX2 (FlashAttention-4's trick): 0 -> 817, 1 -> 865, 2 -> 800, 3 -> 740, 4 -> 713;
-  //                D=128: 1100 / 1160 / 1140; D=32: 414 / 426; D=96: 912 / 920.  Default 1 (value 0), 7 = none.
+  //                D = 128: 1144 / 1209 / 1155; D = 32: 414 / 426; D = 96: 912 / 920.  Default 1 (value 0), 7 = none.
   //   0x800        older spelling of "3 of 8".
+  //   0x20000      D = 64 only: one shared S buffer as for D = 128 (forced ping-pong of the two tiles): 2 % slower.
+  // Tried and removed (kept out of the build): two threads per query row (16 softmax warps, 96 registers): D = 64
+  // 829 vs 799, D = 128 1217 vs 1211 - within noise for twice the softmax code; an event-driven MMA issue loop
+  // (non-blocking mbarrier probes, whichever tile is ready): slower, the single issuing thread becomes the bottleneck.
   const int pingpong = (variant & 0x200) ? 1 : 0;
   const int poly_sel = (variant >> 14) & 7;
   const int poly = poly_sel == 7 ? 0 : (poly_sel ? min(4, poly_sel) : ((variant & 0x800) ? 3 : 1));
   const int np_sel = (variant >> 12) & 3;  // 0 default, 1 -> 1 piece, 2 -> 2 pieces, 3 -> 4 pieces
-  const int np = np_sel == 0 ? kDefaultPieces : (np_sel == 3 ? 4 : np_sel);
+  const int np = np_sel == 3 ? 4 : np_sel;  // 0 = the configuration's default
   if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_fa2_fwd_f16: null pointer");
   if (B < 1 || H < 1 || N < 1 || N > INT32_MAX || B * H > 65535)
     return set_error(B200K_ESHAPE, "b200k_fa2_fwd_f16: need B,H,N >= 1 and B*H <= 65535 (got B=%lld H=%lld N=%lld)",
@@ -563,16 +618,21 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
       case 32: return launch_fa2<Fa2Cfg<32, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
       case 64: return launch_fa2<Fa2Cfg<64, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
       case 96: return launch_fa2<Fa2Cfg<96, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
-      default: return launch_fa2<Fa2Cfg<128, 128, 2, true, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
+      default: return launch_fa2<Fa2Cfg<128, 128, 2, true, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
     }
   }
   switch (D) {
     case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
-    case 64: return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
+    case 64:
+      if (variant & 0x20000)  // one shared S buffer (forced ping-pong of the two tiles) as for D = 128: 2 % slower here
+        return launch_fa2<Fa2Cfg<64, 128, 4, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
+      return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
     case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
     default:
-      if (variant & 0x400) return launch_fa2<Fa2Cfg<128, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
-      return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
+      // 0x400: the older layout for D = 128 (P aliases S, S0 S1 O0 O1) instead of the shared S buffer
+      if (variant & 0x400)
+        return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
+      return launch_fa2<Fa2Cfg<128, 128, 2, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
   }
 }
 

@@ -14,7 +14,9 @@ fn = ops.ffpa_fwd if kern == "ffpa" else ops.fa2_fwd
 s_ = (q[:1, :1].float() @ k[:1, :1].float().transpose(-1, -2)) / D ** 0.5
 ref = torch.softmax(s_, -1) @ v[:1, :1].float()
 fl = 4.0 * B * H * N * N * D
-for rep in range(2):
+import statistics
+res = {v: [] for v in variants}
+for rep in range(int(os.environ.get('REPS', '2'))):
     for var in variants:
         o.zero_()
         fn(q, k, v, o, variant=var)
@@ -27,4 +29,7 @@ for rep in range(2):
         for _ in range(8): fn(q, k, v, o, variant=var)
         e1.record(); torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / 8
+        res[var].append(fl / t * 1e-9)
         print("%s D=%d variant 0x%x: %.3f ms %.0f TFLOPS ok=%s" % (kern, D, var, t, fl / t * 1e-9, ok), flush=True)
+for var in variants:
+    print("MEDIAN %s D=%d variant 0x%x: %.0f TFLOPS (min %.0f max %.0f)" % (kern, D, var, statistics.median(res[var]), min(res[var]), max(res[var])))
