@@ -446,8 +446,12 @@ extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, v
   const int slices = int((D + 255) / 256);
   dim3 grid(unsigned((N + 127) / 128), unsigned(slices), unsigned(BH));
   const float scale_log2 = scale * 1.4426950408889634f;
-  // two softmax warpgroups per row when the tile is exponent-bound (small D); variant bit 32 flips the choice
-  const bool split = ((D <= 256) ? 1 : 0) ^ ((variant & 32) ? 1 : 0);
+  // Two softmax warpgroups per tile (two threads per query row) is an option (variant bit 32).  It paid off before the
+  // row max moved to FMNMX3 and the role loops to a single elected lane; since then one thread per row is faster:
+  // D = 256 1312 vs 1234 TFLOP/s, D = 320 793 vs 748, D = 384 837 vs 786 (same-process round robin, (1,32,8192,D)).
+  // The kernel is bound by the tensor pipe's operand feed here, not by the softmax: with the softmax skipped entirely
+  // (probe bit 128) D = 256 runs at 1270.
+  const bool split = (variant & 32) != 0;
   const int serial = ((variant & 4) ? 1 : 0) | (((variant >> 6) & 3) << 1);  // bits 6,7: timing probes
   if (q_resident && split) {
     auto kern = ffpa_fwd_tcgen05_kernel<true, 2>;

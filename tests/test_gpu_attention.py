@@ -85,6 +85,20 @@ def test_fa2_experiment_builds_agree_with_oracle(D, variant):
     assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), **TOL)
 
 
+@pytest.mark.parametrize("D,variant", [(256, 32), (256, 2), (256, 4), (256, 8), (512, 1), (512, 2), (512, 33), (320, 32)])
+def test_ffpa_selectable_builds_agree_with_oracle(D, variant):
+    """The non-default FFPA builds (two threads per row, streamed Q, serial issue order, forced 1-CTA / CTA-pair)
+    stay correct: they are the fallbacks and the A/B baselines the design notes quote."""
+    from b200k import ops
+
+    torch.manual_seed(D + variant)
+    q, k, v = [torch.randn(1, 2, 700, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.full_like(q, float("nan"))
+    ops.ffpa_fwd(q, k, v, o, variant=variant)
+    assert torch.isfinite(o).all()
+    assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), **TOL)
+
+
 def test_flash_attn_lib_and_ffpa_drop_in_entry_points():
     import ffpa_attn
     from b200k import flash_attn_lib
