@@ -62,6 +62,17 @@ static inline int grid_for(int64_t work_items, int per_block, int sm_count, int 
 }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// e^(x - m) as ex2.approx.ftz(x * log2e - m * log2e): one FFMA and one MUFU.EX2.  (__expf / expf add a denormal-range
+// test and two predicated multiplies per element, which made the f16 softmax instruction-bound; results below 2^-126
+// flush to zero, the relative error is the 2^-22 of the MUFU unit either way.)
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float exp_sub(float x, float m_log2e) {
+  float y;
+  const float t = fmaf(x, kLog2e, -m_log2e);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t));
+  return y;
+}
+
 // ============================================================================================ elementwise add
 template <typename T>
 struct Vec16;  // 16-byte vector of T
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(kThreads) reduce_sum_kernel(const void* __rest
       for (; i < nvec; i += stride) {
         uint4 u = __ldcs(xv + i);
         float4 v = *reinterpret_cast<float4*>(&u);
-        acc += (expf(v.x) + expf(v.y)) + (expf(v.z) + expf(v.w));
+        acc += (exp_sub(v.x, 0.f) + exp_sub(v.y, 0.f)) + (exp_sub(v.z, 0.f) + exp_sub(v.w, 0.f));
       }
     } else {
       A a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -299,7 +310,7 @@ __global__ void __launch_bounds__(kThreads) reduce_sum_kernel(const void* __rest
     tail_from = nvec * L::N;
   }
   for (int64_t j = tail_from + int64_t(blockIdx.x) * kThreads + threadIdx.x; j < n; j += stride) {
-    if constexpr (EXP) acc += expf(float(L::one(x + j)));
+    if constexpr (EXP) acc += exp_sub(float(L::one(x + j)), 0.f);
     else acc += L::one(x + j);
   }
   __shared__ A s_part[kThreads / 32];
@@ -414,6 +425,7 @@ __global__ void __launch_bounds__(kThreads) row_kernel(const T* __restrict__ x, 
     uint4* yv = reinterpret_cast<uint4*>(y + (live ? row : 0) * int64_t(H));
     float v[MAXV * VN];
     float m = -INFINITY, s = 0.f;
+    float ml2 = 0.f;  // m * log2(e) for the safe softmax, 0 for the plain one
     if (cached) {
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
@@ -429,6 +441,7 @@ __global__ void __launch_bounds__(kThreads) row_kernel(const T* __restrict__ x, 
 #pragma unroll
         for (int e = 0; e < MAXV * VN; ++e) m = fmaxf(m, v[e]);
         m = group_reduce<R, true>(m, s_red);
+        ml2 = m * kLog2e;
       }
       if constexpr (OP == OP_SAFE_SOFTMAX || OP == OP_SOFTMAX) {
 #pragma unroll
@@ -436,7 +449,7 @@ __global__ void __launch_bounds__(kThreads) row_kernel(const T* __restrict__ x, 
           const bool in = (t + i * R) < nvec;
 #pragma unroll
           for (int e = 0; e < VN; ++e) {
-            float ex = in ? __expf(v[i * VN + e] - (OP == OP_SAFE_SOFTMAX ? m : 0.f)) : 0.f;
+            float ex = in ? exp_sub(v[i * VN + e], ml2) : 0.f;
             v[i * VN + e] = ex;
             s += ex;
           }
@@ -463,14 +476,14 @@ __global__ void __launch_bounds__(kThreads) row_kernel(const T* __restrict__ x, 
           for (int e = 0; e < VN; ++e) m = fmaxf(m, f[e]);
         }
         m = group_reduce<R, true>(m, s_red);
+        ml2 = m * kLog2e;
       }
       for (int vi = t; live && vi < nvec; vi += R) {
         float f[VN];
         IO::unpack(xv[vi], f);
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
-          if constexpr (OP == OP_SAFE_SOFTMAX) s += __expf(f[e] - m);
-          else if constexpr (OP == OP_SOFTMAX) s += __expf(f[e]);
+          if constexpr (OP == OP_SAFE_SOFTMAX || OP == OP_SOFTMAX) s += exp_sub(f[e], ml2);
           else s = fmaf(f[e], f[e], s);
         }
       }
@@ -500,8 +513,7 @@ __global__ void __launch_bounds__(kThreads) row_kernel(const T* __restrict__ x, 
         IO::unpack(xv[vi], f);
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
-          if constexpr (OP == OP_SAFE_SOFTMAX) f[e] = __expf(f[e] - m) * scale;
-          else if constexpr (OP == OP_SOFTMAX) f[e] = __expf(f[e]) * scale;
+          if constexpr (OP == OP_SAFE_SOFTMAX || OP == OP_SOFTMAX) f[e] = exp_sub(f[e], ml2) * scale;
           else f[e] = f[e] * scale;
         }
         yv[vi] = IO::pack(f);
@@ -523,10 +535,10 @@ __global__ void __launch_bounds__(kThreads) row_kernel_scalar(const T* __restric
       for (int i = threadIdx.x; i < H; i += kThreads) m = fmaxf(m, float(xr[i]));
       m = group_reduce<kThreads, true>(m, s_red);
     }
+    const float ml2 = (OP == OP_SAFE_SOFTMAX) ? m * kLog2e : 0.f;
     for (int i = threadIdx.x; i < H; i += kThreads) {
       const float f = float(xr[i]);
-      if constexpr (OP == OP_SAFE_SOFTMAX) s += __expf(f - m);
-      else if constexpr (OP == OP_SOFTMAX) s += __expf(f);
+      if constexpr (OP == OP_SAFE_SOFTMAX || OP == OP_SOFTMAX) s += exp_sub(f, ml2);
       else s = fmaf(f, f, s);
     }
     if (!(OP == OP_SOFTMAX && prm.total != nullptr)) s = group_reduce<kThreads, false>(s, s_red);
@@ -539,8 +551,7 @@ __global__ void __launch_bounds__(kThreads) row_kernel_scalar(const T* __restric
     }
     for (int i = threadIdx.x; i < H; i += kThreads) {
       float f = float(xr[i]);
-      if constexpr (OP == OP_SAFE_SOFTMAX) f = __expf(f - m) * scale;
-      else if constexpr (OP == OP_SOFTMAX) f = __expf(f) * scale;
+      if constexpr (OP == OP_SAFE_SOFTMAX || OP == OP_SOFTMAX) f = exp_sub(f, ml2) * scale;
       else f = f * scale;
       yr[i] = T(f);
     }
@@ -574,33 +585,73 @@ static int launch_row(const void* x, void* y, int64_t rows, int64_t H, RowParams
 }
 
 // ============================================================================================ RoPE (f32)
+// sin / cos of an fp32 angle of any size (positions reach 10^5): subtract k * 2 pi with a three-constant Cody-Waite
+// split (exact products for |k| < 2^15), then MUFU.SIN / MUFU.COS on [-pi, pi] (absolute error ~5e-7).  The libdevice
+// sincosf costs ~45 instructions per call, which made the textbook path instruction-bound (4.4 TB/s).
+__device__ __forceinline__ void sincos_reduced(float a, float* sn, float* cs) {
+  const float k = rintf(a * 0.15915494309189535f);
+  float r = fmaf(k, -6.28125f, a);                 // 2 pi = 6.28125 + 1.9353071795864769e-3 (+ rounding term)
+  r = fmaf(k, -1.9350051879882812e-3f, r);
+  r = fmaf(k, -3.0199159819580696e-7f, r);
+  *sn = __sinf(r);
+  *cs = __cosf(r);
+}
+
+constexpr int kRopeMaxPairs = 8192;  // inverse-frequency table in shared memory (hidden <= 16384)
 __global__ void __launch_bounds__(kThreads) rope_f32_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                             int64_t seq_len, int hidden, bool quirk, bool vec) {
   const int pairs = hidden / 2;
-  // inverse frequency theta^(-2p/hidden) evaluated in double: at position 8191 an fp32 exponent costs ~5e-3 rad
+  __shared__ float s_inv_freq[kRopeMaxPairs];
+  // inverse frequency theta^(-2p/hidden) evaluated in double, once per CTA: at position 8191 an fp32 exponent costs
+  // ~5e-3 rad.  Rows longer than the table fall back to computing it per element.
   const double neg2_log2theta_over_h = -2.0 * 13.287712379549449 / double(hidden);  // log2(10000)
+  const bool table = !quirk && pairs <= kRopeMaxPairs;
+  if (table) {
+    for (int p = threadIdx.x; p < pairs; p += kThreads) s_inv_freq[p] = float(exp2(double(p) * neg2_log2theta_over_h));
+    __syncthreads();
+  }
+  auto inv_freq = [&](int p) -> float {
+    return table ? s_inv_freq[p] : float(exp2(double(p) * neg2_log2theta_over_h));
+  };
   if (vec) {
-    // one float4 = two neighbouring pairs
-    const int64_t total = seq_len * int64_t(hidden / 4);
+    // One float4 = two neighbouring pairs.  Rows are walked without any per-element division: a CTA takes
+    // ROWS = max(1, kThreads / per_row) rows at a time, a thread the float4s j, j + kThreads, ... of its row, up to
+    // four loads in flight.
     const int per_row = hidden / 4;
-    for (int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x; i < total; i += int64_t(gridDim.x) * kThreads) {
-      const int64_t pos = i / per_row;
-      const int p0 = int(i - pos * per_row) * 2;
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
-      float s0, c0, s1, c1;
-      if (quirk) {
-        sincosf(float(pos), &s0, &c0);
-        s1 = s0; c1 = c0;
-      } else {
-        sincosf(float(pos) * float(exp2(double(p0) * neg2_log2theta_over_h)), &s0, &c0);
-        sincosf(float(pos) * float(exp2(double(p0 + 1) * neg2_log2theta_over_h)), &s1, &c1);
+    const int tpr = per_row < kThreads ? per_row : kThreads;  // threads per row
+    const int rows_per_cta = kThreads / tpr;
+    const int sub = threadIdx.x / tpr, j0 = threadIdx.x - sub * tpr;
+    if (sub >= rows_per_cta) return;
+    for (int64_t pos = int64_t(blockIdx.x) * rows_per_cta + sub; pos < seq_len; pos += int64_t(gridDim.x) * rows_per_cta) {
+      const float4* xr = reinterpret_cast<const float4*>(x + pos * int64_t(hidden));
+      float4* orow = reinterpret_cast<float4*>(out + pos * int64_t(hidden));
+      float sq, cq;
+      if (quirk) sincos_reduced(float(pos), &sq, &cq);
+      for (int jb = j0; jb < per_row; jb += 4 * tpr) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (jb + u * tpr < per_row) v[u] = __ldcs(xr + jb + u * tpr);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = jb + u * tpr;
+          if (j >= per_row) break;
+          float s0, c0, s1, c1;
+          if (quirk) {
+            s0 = s1 = sq;
+            c0 = c1 = cq;
+          } else {
+            sincos_reduced(float(pos) * inv_freq(2 * j), &s0, &c0);
+            sincos_reduced(float(pos) * inv_freq(2 * j + 1), &s1, &c1);
+          }
+          float4 o;
+          o.x = v[u].x * c0 - v[u].y * s0;
+          o.y = v[u].x * s0 + v[u].y * c0;
+          o.z = v[u].z * c1 - v[u].w * s1;
+          o.w = v[u].z * s1 + v[u].w * c1;
+          __stcs(orow + j, o);
+        }
       }
-      float4 o;
-      o.x = v.x * c0 - v.y * s0;
-      o.y = v.x * s0 + v.y * c0;
-      o.z = v.z * c1 - v.w * s1;
-      o.w = v.z * s1 + v.w * c1;
-      __stcs(reinterpret_cast<float4*>(out) + i, o);
     }
   } else {
     const int64_t total = seq_len * int64_t(pairs);
@@ -609,7 +660,7 @@ __global__ void __launch_bounds__(kThreads) rope_f32_kernel(const float* __restr
       const int p = int(i - pos * pairs);
       const float x1 = x[pos * hidden + 2 * p], x2 = x[pos * hidden + 2 * p + 1];
       float sn, cs;
-      sincosf(quirk ? float(pos) : float(pos) * float(exp2(double(p) * neg2_log2theta_over_h)), &sn, &cs);
+      sincos_reduced(quirk ? float(pos) : float(pos) * inv_freq(p), &sn, &cs);
       out[pos * hidden + 2 * p] = x1 * cs - x2 * sn;
       out[pos * hidden + 2 * p + 1] = x1 * sn + x2 * cs;
     }
@@ -635,6 +686,9 @@ __global__ void __launch_bounds__(kThreads) max_i32_kernel(const int* __restrict
 }
 
 constexpr int kSmemBins = 8192;
+// Per-CTA shared-memory bins merged with global atomics at the end (SMEM), or global atomics only (huge bin counts).
+// Four 16-byte loads in flight per thread.  Measured at 128 Mi random 8-bit values: 5.2-5.5 TB/s; giving every lane its
+// own copy of the bins (conflict-free banks) or more CTAs per SM did not move it (4.0-5.5 TB/s over the settings tried).
 template <bool SMEM>
 __global__ void __launch_bounds__(kThreads) histogram_i32_kernel(const int* __restrict__ a, int64_t n,
                                                                  int* __restrict__ hist, int nbins, bool vec) {
@@ -653,9 +707,16 @@ __global__ void __launch_bounds__(kThreads) histogram_i32_kernel(const int* __re
   int64_t done = 0;
   if (vec) {
     const int64_t nvec = n / 4;
-    for (int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x; i < nvec; i += stride) {
-      const int4 v = __ldcs(reinterpret_cast<const int4*>(a) + i);
-      bump(v.x); bump(v.y); bump(v.z); bump(v.w);
+    const int4* av = reinterpret_cast<const int4*>(a);
+    for (int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x; i < nvec; i += 4 * stride) {
+      int4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (i + u * stride < nvec) ? __ldcs(av + i + u * stride) : make_int4(-1, -1, -1, -1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        bump(v[u].x); bump(v[u].y); bump(v[u].z); bump(v[u].w);
+      }
     }
     done = nvec * 4;
   }
@@ -801,7 +862,13 @@ extern "C" int b200k_rope_f32(const void* x, void* out, int64_t seq_len, int64_t
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool vec = (hidden % 4 == 0) && aligned16(x) && aligned16(out);
-  const int grid = grid_for(seq_len * (hidden / (vec ? 4 : 2)), kThreads, di.sm_count, 16);
+  int grid;
+  if (vec) {
+    const int per_row = int(hidden / 4), tpr = per_row < kThreads ? per_row : kThreads;
+    grid = grid_for(seq_len, kThreads / tpr, di.sm_count, 8);  // the kernel walks rows, kThreads / tpr rows per CTA
+  } else {
+    grid = grid_for(seq_len * (hidden / 2), kThreads, di.sm_count, 16);
+  }
   rope_f32_kernel<<<grid, kThreads, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(out), seq_len,
                                             int(hidden), ref_quirk != 0, vec);
   B200K_CHECK_CUDA(cudaGetLastError());
@@ -832,7 +899,7 @@ extern "C" int b200k_histogram_i32(const void* a, int64_t n, void* hist, int64_t
   B200K_CHECK_CUDA(cudaMemsetAsync(hist, 0, size_t(nbins) * sizeof(int), s));
   if (n == 0) return B200K_OK;
   const bool vec = aligned16(a);
-  const int grid = grid_for(n, kThreads * 8, di.sm_count, 4);
+  const int grid = grid_for(n, kThreads * 16, di.sm_count, 4);
   if (nbins <= kSmemBins)
     histogram_i32_kernel<true><<<grid, kThreads, 0, s>>>(static_cast<const int*>(a), n, static_cast<int*>(hist), int(nbins), vec);
   else
