@@ -70,6 +70,9 @@ int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N,
  *   Replaces ffpa_mma_acc_f16_L1 / ffpa_mma_acc_f32_L1, ffpa-attn-mma/csrc/pybind/ffpa_attn_api.cc:L8-17,
  *   launcher ffpa-attn-mma/csrc/cuffpa/launch_templates.cuh:L261-449.
  * scale <= 0 means 1/sqrt(D) (what both references hard-code).
+ * variant: 0 = the shipped configuration.  Other values select experiment / fallback builds of the same math (piece
+ *   counts, polynomial exp2 fraction, TMEM layout, 1-CTA vs CTA-pair FFPA, cycle trace); the bits are listed next to
+ *   the dispatchers in csrc/fa2_fwd_tcgen05.cu and csrc/ffpa_fwd_tcgen05.cu.  Every build is parity-tested.
  */
 int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N,
                       int64_t D, float scale, int v_is_dn, int variant, void* stream);
