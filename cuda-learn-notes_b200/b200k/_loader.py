@@ -29,6 +29,9 @@ F32, F16, BF16, I8, FP8_E4M3, FP8_E5M2, I32 = 0, 1, 2, 3, 4, 5, 6
 
 HGEMM_AUTO, HGEMM_1CTA_128x256, HGEMM_2CTA_256x256, HGEMM_2CTA_256x128 = 0, 1, 2, 3
 
+# activation ops (include/b200k.h)
+ACT_RELU, ACT_SIGMOID, ACT_GELU, ACT_SWISH, ACT_ELU, ACT_HARDSWISH, ACT_HARDSHRINK = range(7)
+
 
 def build(verbose: bool = False) -> str:
     """Compile libb200k.so in-tree with nvcc (seconds; no torch headers involved)."""
@@ -66,6 +69,11 @@ _SIGS = {
     "b200k_histogram_i32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "b200k_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b200k_debug_set_trace": (c_int, [c_void_p]),
+    "b200k_activation": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "b200k_layer_norm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_float, c_int, c_int, c_void_p]),
+    "b200k_dot_prod": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "b200k_mat_transpose_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "b200k_gemv": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
 }
 
 

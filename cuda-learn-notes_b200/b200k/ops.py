@@ -246,5 +246,78 @@ def embedding(idx, weight, out) -> None:
                                      weight.size(1), _DTYPE_ENUM[weight.dtype], _stream(idx)))
 
 
+# ------------------------------------------------------------------------------------------------ support kernels, set 2
+ACT_OPS = {"relu": L.ACT_RELU, "sigmoid": L.ACT_SIGMOID, "gelu": L.ACT_GELU, "swish": L.ACT_SWISH, "elu": L.ACT_ELU,
+           "hardswish": L.ACT_HARDSWISH, "hardshrink": L.ACT_HARDSHRINK}
+
+
+def activation(x, y, op: str, ref_clamp: bool = True) -> None:
+    """y = op(x) elementwise; f32 or f16.  ``ref_clamp`` keeps the reference's input clamp for sigmoid / gelu
+    (kernels/sigmoid/sigmoid.cu:L19-22, kernels/gelu/gelu.cu:L19-22)."""
+    if x.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("values must be torch::kFloat32 or torch::kHalf")
+    _check_dtype(y, x.dtype)
+    if x.numel() != y.numel():
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(x, y)
+    with _DeviceGuard(x):
+        L.check(_lib.b200k_activation(x.data_ptr(), y.data_ptr(), x.numel(), _DTYPE_ENUM[x.dtype], ACT_OPS[op],
+                                      1 if ref_clamp else 0, _stream(x)))
+
+
+def layer_norm(x, y, g: float, b: float, eps: float = 1e-5, eps_inside_k: bool = True) -> None:
+    """Row-wise layer norm with scalar scale / bias, x[N,K] f32 or f16.  ``eps_inside_k`` = the reference's
+    rsqrt(sum/(K + eps)) (kernels/layer-norm/layer_norm.cu:L69)."""
+    if x.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("values must be torch::kFloat32 or torch::kHalf")
+    _check_dtype(y, x.dtype)
+    if x.shape != y.shape or x.dim() != 2:
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(x, y)
+    with _DeviceGuard(x):
+        L.check(_lib.b200k_layer_norm(x.data_ptr(), y.data_ptr(), x.size(0), x.size(1), float(g), float(b), float(eps),
+                                      _DTYPE_ENUM[x.dtype], 1 if eps_inside_k else 0, _stream(x)))
+
+
+def dot_prod(a, b) -> torch.Tensor:
+    """Returns a new 1-element f32 tensor like the reference bindings (kernels/dot-product/dot_product.cu:L233-283)."""
+    if a.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("values must be torch::kFloat32 or torch::kHalf")
+    _check_dtype(b, a.dtype)
+    if a.numel() != b.numel():
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(a, b)
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    with _DeviceGuard(a):
+        L.check(_lib.b200k_dot_prod(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _DTYPE_ENUM[a.dtype],
+                                    _workspace(a.device).data_ptr(), _stream(a)))
+    return out
+
+
+def mat_transpose(x, y) -> None:
+    """y[N,M] = x[M,N]^T, f32 (kernels/mat-transpose/mat_transpose.cu:L296-339)."""
+    _check_dtype(x, torch.float32)
+    _check_dtype(y, torch.float32)
+    if x.dim() != 2 or y.numel() != x.numel():
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(x, y)
+    with _DeviceGuard(x):
+        L.check(_lib.b200k_mat_transpose_f32(x.data_ptr(), y.data_ptr(), x.size(0), x.size(1), _stream(x)))
+
+
+def gemv(a, x, y) -> None:
+    """y[M,1] = a[M,K] @ x[K,1], f32 or f16 with f32 accumulation (kernels/sgemv/sgemv.cu:L126-195, hgemv.cu:L130-199)."""
+    if a.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("values must be torch::kFloat32 or torch::kHalf")
+    _check_dtype(x, a.dtype)
+    _check_dtype(y, a.dtype)
+    if a.dim() != 2 or x.numel() != a.size(1) or y.numel() != a.size(0):
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(a, x, y)
+    with _DeviceGuard(a):
+        L.check(_lib.b200k_gemv(a.data_ptr(), x.data_ptr(), y.data_ptr(), a.size(0), a.size(1), _DTYPE_ENUM[a.dtype],
+                                _stream(a)))
+
+
 def default_scale(D: int) -> float:
     return 1.0 / math.sqrt(D)

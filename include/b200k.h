@@ -128,6 +128,43 @@ int b200k_histogram_i32(const void* a, int64_t n, void* hist, int64_t nbins, voi
 int b200k_embedding(const void* idx, const void* weight, void* out, int64_t n, int64_t rows, int64_t emb, int dtype,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------ support kernels, set 2
+ * (the remaining bandwidth kernels of the reference, same recipe as above.)
+ *
+ * y = f(x) elementwise over n values, dtype B200K_F32 or B200K_F16 (f16 I/O, f32 math).
+ *   kernels/relu/relu.cu:L21-97, sigmoid/sigmoid.cu:L24-136, gelu/gelu.cu:L38-163 (tanh approximation), swish/swish.cu:L20-97,
+ *   elu/elu.cu:L35-120 (alpha = 1), hardswish/hardswish.cu:L36-140, hardshrink/hardshrink.cu:L33-135 (lambda = 0.5); each
+ *   family's six entry points (f32, f32x4, f16, f16x2, f16x8, f16x8_pack) map here.
+ * ref_clamp = 1 reproduces the input clamp of the reference's sigmoid / gelu kernels: x limited to +-88.3762626647949
+ *   (f32 kernels) or to [-9.703125, 11.09375] (f16 kernels: MIN_EXP_F16 / MAX_EXP_F16 as rounded to half) BEFORE the
+ *   function, so the f16 gelu saturates at 11.09375 for large x.  ref_clamp = 0 is the plain function. */
+#define B200K_ACT_RELU 0
+#define B200K_ACT_SIGMOID 1
+#define B200K_ACT_GELU 2
+#define B200K_ACT_SWISH 3
+#define B200K_ACT_ELU 4
+#define B200K_ACT_HARDSWISH 5
+#define B200K_ACT_HARDSHRINK 6
+int b200k_activation(const void* x, void* y, int64_t n, int dtype, int op, int ref_clamp, void* stream);
+
+/* y = (x - mean(x)) * rsqrt(v) * g + b for each row of x[N,K]; scalar g, b; dtype F32 or F16 (f32 math).
+ * kernels/layer-norm/layer_norm.cu:L48-419, bindings L732-812.  eps_inside_k = 1 reproduces the reference:
+ * v = sum((x-mean)^2) / (K + eps) (L69, L103, L187 ...); eps_inside_k = 0 is the textbook v = sum(..)/K + eps. */
+int b200k_layer_norm(const void* x, void* y, int64_t N, int64_t K, float g, float b, float eps, int dtype,
+                     int eps_inside_k, void* stream);
+
+/* out[0] = sum_i a[i] * b[i] (f32 result, f32 accumulation; dtype F32 or F16).  kernels/dot-product/dot_product.cu:L20-184,
+ * bindings L233-283.  Deterministic (fixed two-pass order) where the reference uses atomicAdd.  `out`: 1-element f32
+ * device buffer; `workspace`: >= b200k_reduce_workspace_bytes(). */
+int b200k_dot_prod(const void* a, const void* b, void* out, int64_t n, int dtype, void* workspace, void* stream);
+
+/* y[N,M] = transpose(x[M,N]), fp32.  kernels/mat-transpose/mat_transpose.cu:L20-278 (13 entry points, L296-359). */
+int b200k_mat_transpose_f32(const void* x, void* y, int64_t M, int64_t N, void* stream);
+
+/* y[M] = A[M,K] x[K], dtype F32 or F16 (f32 accumulation; the reference's hgemv accumulates in half).
+ * kernels/sgemv/sgemv.cu:L20-104 (sgemv_k32_f32, sgemv_k128_f32x4, sgemv_k16_f32), kernels/hgemv/hgemv.cu:L24-108. */
+int b200k_gemv(const void* a, const void* x, void* y, int64_t M, int64_t K, int dtype, void* stream);
+
 /* Debug hook, not part of the drop-in surface: device buffer of 3*32*8 uint64 that the next traced FA-2 launch
  * (variant | 0x100, D = 64 or 128) fills with clock64() stamps of CTA (0,0); see tools/gpu_trace_fa2.py. */
 int b200k_debug_set_trace(void* dev_u64_buffer);

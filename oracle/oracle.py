@@ -166,3 +166,63 @@ def histogram(a) -> np.ndarray:
 def embedding(idx, weight):
     """out[i,:] = weight[idx[i],:] (kernels/embedding/embedding.cu:L16-119) — exact copy."""
     return weight.cpu()[idx.cpu().long()]
+
+
+# ------------------------------------------------------------------------------------------------ support kernels, set 2
+# (SURVEY.md section 8f-3)  All in float64 on the CPU; f16 inputs are taken as the exact values they hold.
+_CLAMP_F32 = 88.3762626647949          # MAX_EXP_F32 / -MIN_EXP_F32 (sigmoid.cu:L19-20, gelu.cu:L19-20)
+_CLAMP_F16 = (-9.703125, 11.09375)     # MIN_EXP_F16 / MAX_EXP_F16 as rounded to half (sigmoid.cu:L21-22, gelu.cu:L21-22)
+
+
+def activation(x, op: str, ref_clamp: bool = True):
+    """The seven activation families.  relu.cu:L21-24, sigmoid.cu:L27-35, gelu.cu:L38-52 (tanh approximation: the
+    default GELU_OPS / HALF_GELU_OPS), swish.cu:L20-22, elu.cu:L41-43 (alpha = 1), hardswish.cu:L36-44,
+    hardshrink.cu:L33-39 (lambda = 0.5).  ref_clamp restates the input clamp the sigmoid and gelu kernels apply first
+    (per input dtype: the f32 kernels clamp to +-88.376, the f16 kernels to [-9.703, 11.094])."""
+    xf = x.detach().cpu().double()
+    if ref_clamp and op in ("sigmoid", "gelu"):
+        if x.dtype == torch.float16:
+            xf = xf.clamp(_CLAMP_F16[0], _CLAMP_F16[1])
+        else:
+            xf = xf.clamp(-_CLAMP_F32, _CLAMP_F32)
+    if op == "relu":
+        return xf.clamp_min(0.0)
+    if op == "sigmoid":
+        return 1.0 / (1.0 + torch.exp(-xf))
+    if op == "gelu":
+        return 0.5 * xf * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (xf + 0.044715 * xf ** 3)))
+    if op == "swish":
+        return xf / (1.0 + torch.exp(-xf))
+    if op == "elu":
+        return torch.where(xf > 0, xf, torch.exp(xf) - 1.0)
+    if op == "hardswish":
+        return torch.where(xf >= 3.0, xf, torch.where(xf <= -3.0, torch.zeros_like(xf), xf * (xf + 3.0) / 6.0))
+    if op == "hardshrink":
+        return torch.where((xf > 0.5) | (xf < -0.5), xf, torch.zeros_like(xf))
+    raise ValueError(op)
+
+
+def layer_norm(x, g: float = 1.0, b: float = 0.0, eps: float = 1e-5, eps_inside_k: bool = True):
+    """y = (x - mean) * rsqrt(v) * g + b per row (layer_norm.cu:L54-73).  eps_inside_k=True restates the reference's
+    v = sum((x-mean)^2) / (K + eps) (L69); False is the textbook sum/K + eps (script oracle layer_norm.py: F.layer_norm)."""
+    xf = x.detach().cpu().double()
+    K = xf.shape[-1]
+    d = xf - xf.mean(-1, keepdim=True)
+    ss = d.pow(2).sum(-1, keepdim=True)
+    v = ss / (K + eps) if eps_inside_k else ss / K + eps
+    return d * torch.rsqrt(v) * g + b
+
+
+def dot_prod(a, b) -> float:
+    """sum(a * b) (dot_product.cu:L35-53), exact products, float64 accumulation."""
+    return float((a.detach().cpu().double().flatten() * b.detach().cpu().double().flatten()).sum())
+
+
+def mat_transpose(x):
+    """y[N,M] = x[M,N]^T (mat_transpose.cu:L29-37) - a pure permutation, bit-exact."""
+    return x.detach().cpu().t().contiguous()
+
+
+def gemv(a, x):
+    """y = a @ x (sgemv.cu:L32-52, hgemv.cu:L34-52) in float64."""
+    return a.detach().cpu().double() @ x.detach().cpu().double().reshape(-1, 1)

@@ -112,3 +112,38 @@ def test_elementwise_and_embedding_exact():
     w = torch.randn(50, 8)
     idx = torch.randint(0, 50, (20,), dtype=torch.int32)
     assert torch.equal(oracle.embedding(idx, w), w[idx.long()])
+
+
+def test_second_set_oracles_match_the_comparators_the_reference_scripts_print():
+    """The reference's scripts for these kernels print their outputs next to a torch comparator (no assertion):
+    torch.nn.GELU("tanh") (gelu.py:L62), torch.sigmoid (sigmoid.py:L70), x * sigmoid(x) (swish.py:L59),
+    where(x > 0, x, exp(x) - 1) (elu.py:L50), F.hardswish / F.hardshrink(lambd=0.5) (hardswish.py:L51, hardshrink.py:L51),
+    torch.dot, torch.matmul, x.t().  The oracle's plain mode (no reference clamp) has to agree with them."""
+    import torch.nn.functional as F
+
+    torch.manual_seed(11)
+    x = (torch.randn(4096) * 4).double()
+    pairs = {
+        "relu": torch.relu(x), "sigmoid": torch.sigmoid(x), "gelu": F.gelu(x, approximate="tanh"), "swish": x * torch.sigmoid(x),
+        "elu": torch.where(x > 0, x, torch.exp(x) - 1), "hardswish": F.hardswish(x), "hardshrink": F.hardshrink(x, lambd=0.5),
+    }
+    for op, want in pairs.items():
+        assert torch.allclose(oracle.activation(x, op, ref_clamp=False), want, rtol=1e-12, atol=1e-14), op
+    # the reference clamp only changes values outside the clamp range
+    inside = x.abs() < 9.0
+    for op in ("sigmoid", "gelu"):
+        a, b = oracle.activation(x.half(), op, ref_clamp=True), oracle.activation(x.half(), op, ref_clamp=False)
+        assert torch.equal(a[inside], b[inside])
+    assert float(oracle.activation(torch.tensor([20.0]).half(), "gelu")[0]) == 11.09375
+    assert float(oracle.activation(torch.tensor([20.0]), "gelu")[0]) == 20.0  # the f32 clamp is at 88.4
+
+    m = torch.randn(37, 300).double()
+    assert torch.allclose(oracle.layer_norm(m, 1.0, 0.0, 1e-5, eps_inside_k=False), F.layer_norm(m, (300,), eps=1e-5),
+                          rtol=1e-10, atol=1e-12)
+    # the reference's form (eps added to K) differs from the textbook one by a relative 1e-5/K, i.e. not at all in fp32
+    assert torch.allclose(oracle.layer_norm(m, 1.5, -0.5, 1e-5, True), oracle.layer_norm(m, 1.5, -0.5, 0.0, False), rtol=1e-6)
+    a, b = torch.randn(1000).double(), torch.randn(1000).double()
+    assert abs(oracle.dot_prod(a, b) - float(torch.dot(a, b))) < 1e-10
+    assert torch.equal(oracle.mat_transpose(m), m.t().contiguous())
+    v = torch.randn(300, 1).double()
+    assert torch.allclose(oracle.gemv(m, v), m @ v)

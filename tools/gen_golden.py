@@ -43,6 +43,15 @@ def main():
         "rope_lib": mdefs("kernels/rope/rope.cu"),
         "hist_lib": mdefs("kernels/histogram/histogram.cu"),
         "embedding_lib": mdefs("kernels/embedding/embedding.cu"),
+        # second set
+        "relu_lib": mdefs("kernels/relu/relu.cu"), "sigmoid_lib": mdefs("kernels/sigmoid/sigmoid.cu"),
+        "gelu_lib": mdefs("kernels/gelu/gelu.cu"), "swish_lib": mdefs("kernels/swish/swish.cu"),
+        "elu_lib": mdefs("kernels/elu/elu.cu"), "hardswish_lib": mdefs("kernels/hardswish/hardswish.cu"),
+        "hardshrink_lib": mdefs("kernels/hardshrink/hardshrink.cu"),
+        "layer_norm_lib": mdefs("kernels/layer-norm/layer_norm.cu"),
+        "dot_product_lib": mdefs("kernels/dot-product/dot_product.cu"),
+        "mat_transpose_lib": mdefs("kernels/mat-transpose/mat_transpose.cu"),
+        "sgemv_lib": mdefs("kernels/sgemv/sgemv.cu"), "hgemv_lib": mdefs("kernels/hgemv/hgemv.cu"),
     }
     # macro-generated binding names the regex cannot see
     red = open(os.path.join(REF, "kernels/reduce/block_all_reduce.cu")).read()

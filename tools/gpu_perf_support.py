@@ -53,6 +53,8 @@ def main():
     idx = torch.randint(0, 131072, (262144,), dtype=torch.int32, device=dev)
     eo = torch.empty(262144, 1024, dtype=torch.half, device=dev)
     hin = torch.randint(0, 256, (n,), dtype=torch.int32, device=dev)
+    gx32, gy32 = torch.randn(4096, 1, device=dev), torch.empty(32768, 1, device=dev)
+    gx16, gy16 = torch.randn(8192, 1, dtype=torch.half, device=dev), torch.empty(32768, 1, dtype=torch.half, device=dev)
     cases = [
         ("elementwise_add_f32", lambda: ops.elementwise_add(a, b, c), 3 * n * 4),
         ("elementwise_add_f16", lambda: ops.elementwise_add(ah, bh, ch), 3 * n * 2),
@@ -69,6 +71,22 @@ def main():
         ("rope_f32_textbook", lambda: ops.rope_f32(x32, y32, False), 2 * x32.numel() * 4),
         ("embedding_f16_e1024", lambda: ops.embedding(idx, w, eo), 2 * eo.numel() * 2 + idx.numel() * 4),
         ("histogram_i32_256bins", lambda: ops.histogram_i32(hin, nbins=256), n * 4),
+        # second set
+        ("relu_f32", lambda: ops.activation(a, c, "relu"), 2 * n * 4),
+        ("gelu_f32", lambda: ops.activation(a, c, "gelu"), 2 * n * 4),
+        ("sigmoid_f16", lambda: ops.activation(ah, ch, "sigmoid"), 2 * n * 2),
+        ("gelu_f16", lambda: ops.activation(ah, ch, "gelu"), 2 * n * 2),
+        ("swish_f16", lambda: ops.activation(ah, ch, "swish"), 2 * n * 2),
+        ("elu_f16", lambda: ops.activation(ah, ch, "elu"), 2 * n * 2),
+        ("hardswish_f16", lambda: ops.activation(ah, ch, "hardswish"), 2 * n * 2),
+        ("layer_norm_f16_k8192", lambda: ops.layer_norm(x16, y16, 1.0, 0.0), 2 * x16.numel() * 2),
+        ("layer_norm_f16_k1024", lambda: ops.layer_norm(xs, ys, 1.0, 0.0), 2 * xs.numel() * 2),
+        ("layer_norm_f32_k4096", lambda: ops.layer_norm(x32, y32, 1.0, 0.0), 2 * x32.numel() * 4),
+        ("dot_prod_f32", lambda: ops.dot_prod(a, b), 2 * n * 4),
+        ("dot_prod_f16", lambda: ops.dot_prod(ah, bh), 2 * n * 2),
+        ("mat_transpose_f32_32768x4096", lambda: ops.mat_transpose(x32, y32.view(4096, 32768)), 2 * x32.numel() * 4),
+        ("sgemv_32768x4096", lambda: ops.gemv(x32, gx32, gy32), x32.numel() * 4),
+        ("hgemv_32768x8192", lambda: ops.gemv(x16, gx16, gy16), x16.numel() * 2),
     ]
     for name, fn, nbytes in cases:
         t = timeit(fn, args.iters)
