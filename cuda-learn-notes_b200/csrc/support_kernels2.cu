@@ -67,22 +67,27 @@ __global__ void __launch_bounds__(kThreads) activation_kernel(const T* __restric
   const int64_t stride = int64_t(gridDim.x) * kThreads;
   int64_t done = 0;
   if (vec) {
+    // A CTA walks chunks of 4 * kThreads consecutive 16-byte vectors; inside a full chunk the four loads of a thread are
+    // at compile-time offsets from one base pointer (no per-load index arithmetic or bounds test).
     const int64_t nvec = n / VN;
-    const uint4* xv = reinterpret_cast<const uint4*>(x);
-    uint4* yv = reinterpret_cast<uint4*>(y);
-    for (int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x; i < nvec; i += 4 * stride) {
+    constexpr int64_t CH = 4 * kThreads;
+    for (int64_t base = int64_t(blockIdx.x) * CH; base < nvec; base += int64_t(gridDim.x) * CH) {
+      const uint4* xv = reinterpret_cast<const uint4*>(x) + base + threadIdx.x;
+      uint4* yv = reinterpret_cast<uint4*>(y) + base + threadIdx.x;
+      const bool full = base + CH <= nvec;
+      const int64_t left = nvec - base - threadIdx.x;  // vectors from this thread's first one to the end
       uint4 u[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (i + k * stride < nvec) u[k] = __ldcs(xv + i + k * stride);
+        if (full || k * kThreads < left) u[k] = __ldcs(xv + k * kThreads);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (i + k * stride >= nvec) break;
+        if (!full && k * kThreads >= left) break;
         float f[VN];
         IO::unpack(u[k], f);
 #pragma unroll
         for (int e = 0; e < VN; ++e) f[e] = act<T, OP, CLAMP>(f[e]);
-        __stcs(yv + i + k * stride, IO::pack(f));
+        __stcs(yv + k * kThreads, IO::pack(f));
       }
     }
     done = nvec * VN;
@@ -97,7 +102,8 @@ static int launch_act2(const void* x, void* y, int64_t n, bool clamp, cudaStream
   const int grid = grid_for(vec ? n / RowIO<T>::N : n, kThreads * 4, di.sm_count, 8);
   const T* xp = static_cast<const T*>(x);
   T* yp = static_cast<T*>(y);
-  if (clamp && (OP == B200K_ACT_SIGMOID || OP == B200K_ACT_GELU))
+  // (the f32 sigmoid clamp at +-88.4 cannot change a flush-to-zero fp32 result: skip its two instructions per value)
+  if (clamp && ((OP == B200K_ACT_SIGMOID && sizeof(T) == 2) || OP == B200K_ACT_GELU))
     activation_kernel<T, OP, true><<<grid, kThreads, 0, s>>>(xp, yp, n, vec);
   else
     activation_kernel<T, OP, false><<<grid, kThreads, 0, s>>>(xp, yp, n, vec);
@@ -335,23 +341,47 @@ __global__ void __launch_bounds__(kThreads) dot_kernel(const T* __restrict__ a, 
 // reads and writes are both full 256-byte row segments.  The reference's 13 entry points differ only in their index
 // arithmetic (mat_transpose.cu:L29-278).
 constexpr int kTile = 64;
+template <bool VEC4>
 __global__ void __launch_bounds__(kThreads) transpose_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int M,
                                                                  int N, int tiles_n, int64_t tiles) {
   __shared__ float tile[kTile][kTile + 1];
-  const int tx = threadIdx.x % kTile, ty = threadIdx.x / kTile;  // 64 x 4
   for (int64_t tidx = blockIdx.x; tidx < tiles; tidx += gridDim.x) {
     const int tm = int(tidx / tiles_n), tn = int(tidx - int64_t(tm) * tiles_n);
     const int m0 = tm * kTile, n0 = tn * kTile;
+    if constexpr (VEC4) {
+      // M % 4 == 0, N % 4 == 0, 16-byte aligned bases: 16-byte loads and stores, all four loads of a thread in flight
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + k * kThreads, r = idx >> 4, c = (idx & 15) * 4;
+        if (m0 + r < M && n0 + c < N) v[k] = __ldcs(reinterpret_cast<const float4*>(x + int64_t(m0 + r) * N + n0 + c));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + k * kThreads, r = idx >> 4, c = (idx & 15) * 4;
+        tile[r][c] = v[k].x; tile[r][c + 1] = v[k].y; tile[r][c + 2] = v[k].z; tile[r][c + 3] = v[k].w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + k * kThreads, r = idx >> 4, c = (idx & 15) * 4;  // r: column of x, c: row of x
+        if (n0 + r < N && m0 + c < M)
+          __stcs(reinterpret_cast<float4*>(y + int64_t(n0 + r) * M + m0 + c),
+                 make_float4(tile[c][r], tile[c + 1][r], tile[c + 2][r], tile[c + 3][r]));
+      }
+    } else {
+      const int tx = threadIdx.x % kTile, ty = threadIdx.x / kTile;  // 64 x 4
 #pragma unroll 4
-    for (int r = ty; r < kTile; r += kThreads / kTile) {
-      const int m = m0 + r, nn = n0 + tx;
-      if (m < M && nn < N) tile[r][tx] = __ldcs(x + int64_t(m) * N + nn);
-    }
-    __syncthreads();
+      for (int r = ty; r < kTile; r += kThreads / kTile) {
+        const int m = m0 + r, nn = n0 + tx;
+        if (m < M && nn < N) tile[r][tx] = __ldcs(x + int64_t(m) * N + nn);
+      }
+      __syncthreads();
 #pragma unroll 4
-    for (int r = ty; r < kTile; r += kThreads / kTile) {
-      const int nn = n0 + r, m = m0 + tx;
-      if (nn < N && m < M) __stcs(y + int64_t(nn) * M + m, tile[tx][r]);
+      for (int r = ty; r < kTile; r += kThreads / kTile) {
+        const int nn = n0 + r, m = m0 + tx;
+        if (nn < N && m < M) __stcs(y + int64_t(nn) * M + m, tile[tx][r]);
+      }
     }
     __syncthreads();
   }
@@ -472,8 +502,12 @@ extern "C" int b200k_mat_transpose_f32(const void* x, void* y, int64_t M, int64_
   const int tiles_m = int((M + kTile - 1) / kTile), tiles_n = int((N + kTile - 1) / kTile);
   const int64_t tiles = int64_t(tiles_m) * tiles_n;
   const int grid = grid_for(tiles, 1, di.sm_count, 16);
-  transpose_f32_kernel<<<grid, kThreads, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y), int(M), int(N),
-                                                tiles_n, tiles);
+  const float* xp = static_cast<const float*>(x);
+  float* yp = static_cast<float*>(y);
+  if (M % 4 == 0 && N % 4 == 0 && aligned16(x) && aligned16(y))
+    transpose_f32_kernel<true><<<grid, kThreads, 0, s>>>(xp, yp, int(M), int(N), tiles_n, tiles);
+  else
+    transpose_f32_kernel<false><<<grid, kThreads, 0, s>>>(xp, yp, int(M), int(N), tiles_n, tiles);
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;
 }
