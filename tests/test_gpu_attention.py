@@ -23,7 +23,10 @@ def _run(q, k, v):
 @pytest.mark.parametrize("shape", [(1, 2, 256, 64), (1, 1, 128, 64), (2, 3, 1000, 64), (1, 1, 77, 64), (1, 1, 1, 64),
                                    (1, 2, 384, 128), (2, 2, 1000, 128), (1, 2, 512, 32), (1, 2, 333, 32),
                                    (1, 2, 512, 96), (1, 2, 333, 96), (1, 2, 256, 256), (1, 2, 1000, 256),
-                                   (1, 2, 512, 512), (1, 1, 384, 320), (1, 1, 300, 192), (1, 1, 256, 1024), (1, 1, 200, 768)])
+                                   (1, 2, 512, 512), (1, 1, 384, 320), (1, 1, 300, 192), (1, 1, 256, 1024), (1, 1, 200, 768),
+                                   # one and two KV tiles, ragged, for every FA-2 layout (D = 128 shares one S buffer)
+                                   (1, 1, 1, 128), (1, 1, 100, 128), (1, 2, 128, 128), (1, 2, 129, 128), (1, 1, 257, 128),
+                                   (1, 1, 64, 96), (1, 1, 65, 96), (1, 1, 5, 32), (1, 1, 130, 32), (1, 1, 3, 256), (1, 1, 129, 512)])
 def test_attention_vs_oracle(shape):
     B, H, N, D = shape
     torch.manual_seed(N + D)
