@@ -9,7 +9,8 @@ cp -r $REF/kernels/hgemm/hgemm.py $REF/kernels/hgemm/tools $DST/kernels/hgemm/
 cp $REF/kernels/flash-attn/flash_attn_mma.py $DST/kernels/flash-attn/
 cp $REF/ffpa-attn-mma/env.py $DST/ffpa-attn-mma/
 cp $REF/ffpa-attn-mma/tests/test_ffpa_attn.py $DST/ffpa-attn-mma/tests/
-for d in elementwise reduce softmax rms-norm rope histogram embedding; do
+for d in elementwise reduce softmax rms-norm rope histogram embedding \
+         relu sigmoid gelu swish elu hardswish hardshrink layer-norm dot-product mat-transpose sgemv hgemv; do
   mkdir -p $DST/kernels/$d; cp $REF/kernels/$d/*.py $DST/kernels/$d/
 done
 echo staged under $DST
