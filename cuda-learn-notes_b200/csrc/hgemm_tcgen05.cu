@@ -20,7 +20,8 @@
 
 namespace b200k {
 
-template <int CG_, int BN_, bool B_MN_, int STAGES_>
+// DT: 0 = fp16, 1 = bf16 (both kind::f16, 16-bit output), 2 = tf32 (kind::tf32 on fp32 operands, fp32 output)
+template <int CG_, int BN_, bool B_MN_, int STAGES_, int DT_ = 0>
 struct GemmCfg {
   static constexpr int CG = CG_;
   static constexpr int BN = BN_;
@@ -28,10 +29,14 @@ struct GemmCfg {
   static constexpr int STAGES = STAGES_;
   static constexpr int BM_CTA = 128;
   static constexpr int BM = BM_CTA * CG;
-  static constexpr int BK = 64;
+  static constexpr int DT = DT_;
+  static constexpr int ELEM = (DT_ == 2) ? 4 : 2;       // bytes per operand / output element
+  static constexpr int BK = 128 / ELEM;                // one 128-byte swizzle row of K per stage: 64 halves or 32 floats
+  static constexpr int UMMA_K = 32 / ELEM;             // K of one tcgen05.mma: 32 bytes
+  static constexpr int ROW_ELEMS = 128 / ELEM;         // elements of a 128-byte shared-memory row (MN-major boxes, C staging)
   static constexpr int BN_CTA = BN / CG;  // rows of B (N index) each CTA stages
-  static constexpr int A_BYTES = BM_CTA * BK * 2;
-  static constexpr int B_BYTES = BN_CTA * BK * 2;
+  static constexpr int A_BYTES = BM_CTA * 128;
+  static constexpr int B_BYTES = BN_CTA * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARP_BYTES = 2 * 32 * 128;  // two 32-row x 128-byte buffers per epilogue warp
   static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
@@ -136,8 +141,8 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tma_load_2d_2sm(sa, &tmA, fb, k0, m0, policy_a);
             if constexpr (B_MN) {
 #pragma unroll
-              for (int j = 0; j < Cfg::BN_CTA / 64; ++j)
-                tma_load_2d_2sm(sb + j * 8192, &tmB, fb, n0 + j * 64, k0, policy_b);
+              for (int j = 0; j < Cfg::BN_CTA / Cfg::ROW_ELEMS; ++j)
+                tma_load_2d_2sm(sb + j * Cfg::BK * 128, &tmB, fb, n0 + j * Cfg::ROW_ELEMS, k0, policy_b);
             } else {
               tma_load_2d_2sm(sb, &tmB, fb, k0, n0, policy_b);
             }
@@ -146,8 +151,8 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tma_load_2d(sa, &tmA, fb_local, k0, m0, policy_a);
             if constexpr (B_MN) {
 #pragma unroll
-              for (int j = 0; j < Cfg::BN_CTA / 64; ++j)
-                tma_load_2d(sb + j * 8192, &tmB, fb_local, n0 + j * 64, k0, policy_b);
+              for (int j = 0; j < Cfg::BN_CTA / Cfg::ROW_ELEMS; ++j)
+                tma_load_2d(sb + j * Cfg::BK * 128, &tmB, fb_local, n0 + j * Cfg::ROW_ELEMS, k0, policy_b);
             } else {
               tma_load_2d(sb, &tmB, fb_local, k0, n0, policy_b);
             }
@@ -162,13 +167,13 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
     // Whole warp convergent; tcgen05.mma / commit issued by one elected lane.
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_f16(Cfg::BM, BN, /*acc_f32=*/true, /*a_mn=*/false, /*b_mn=*/B_MN);
+      constexpr uint32_t idesc = make_idesc(Cfg::BM, BN, /*operand format: f16, bf16, tf32*/ Cfg::DT, /*a_mn=*/false, /*b_mn=*/B_MN);
       // A: K-major, rows 128 B apart, 8-row groups 1024 B apart.
       constexpr uint64_t a_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);
-      // B (TN): same K-major layout.  B (NN): MN-major, 64 N-elements per 128 B row, 8 K-rows per 1024 B atom (SBO),
-      // next 64 N-elements one TMA box (64 rows x 128 B = 8192 B) further (LBO).
-      constexpr uint64_t b_hi = B_MN ? make_smem_desc_hi(8192, 1024, kSwizzle128B) : make_smem_desc_hi(16, 1024, kSwizzle128B);
-      constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;  // bytes per UMMA_K = 16
+      // B (TN): same K-major layout.  B (NN): MN-major, one 128 B row = 64 (32 for tf32) N-elements, 8 K-rows per
+      // 1024 B atom (SBO), the next row-full of N-elements one TMA box (BK rows x 128 B) further (LBO).
+      constexpr uint64_t b_hi = B_MN ? make_smem_desc_hi(Cfg::BK * 128, 1024, kSwizzle128B) : make_smem_desc_hi(16, 1024, kSwizzle128B);
+      constexpr uint32_t b_kstep = B_MN ? uint32_t(Cfg::UMMA_K) * 128u : 32u;  // bytes per UMMA K step
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -185,10 +190,10 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const uint32_t sb = sa + Cfg::A_BYTES;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < Cfg::BK / 16; ++k) {
+            for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; ++k) {
               const uint64_t adesc = smem_desc(a_hi, sa + k * 32);
               const uint64_t bdesc = smem_desc(b_hi, sb + k * b_kstep);
-              umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss<CG, (Cfg::DT == 2)>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             if constexpr (CG == 2) umma_commit_2sm(bar_empty + 8 * stage, 0b11);
             else umma_commit(bar_empty + 8 * stage);
@@ -216,14 +221,16 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int row0 = tm * Cfg::BM + int(cta_rank) * Cfg::BM_CTA + int(q) * 32;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
+      // one chunk = 32 rows x 128 bytes of C per warp: 64 columns of 16-bit output or 32 columns of fp32
+      constexpr int CC = Cfg::ROW_ELEMS;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        uint32_t r[64];
-        const uint32_t taddr = tmem_addr(tmem_base, q * 32, acc * BN + c * 64);
+      for (int c = 0; c < BN / CC; ++c) {
+        uint32_t r[CC];
+        const uint32_t taddr = tmem_addr(tmem_base, q * 32, acc * BN + c * CC);
         tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_32x32b_x32(taddr + 32, r + 32);
+        if constexpr (CC == 64) tmem_ld_32x32b_x32(taddr + 32, r + 32);
         tmem_wait_ld();
-        if (c == BN / 64 - 1) {
+        if (c == BN / CC - 1) {
           // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -239,15 +246,25 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t row_addr = buf + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float* f = reinterpret_cast<const float*>(r + 8 * j);
-          st_shared_v4(row_addr + ((j ^ (lane & 7)) << 4), pack_half2(f[0], f[1]), pack_half2(f[2], f[3]),
-                       pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
+          if constexpr (Cfg::DT == 2) {
+            st_shared_v4(row_addr + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          } else {
+            const float* f = reinterpret_cast<const float*>(r + 8 * j);
+            if constexpr (Cfg::DT == 1)
+              st_shared_v4(row_addr + ((j ^ (lane & 7)) << 4), pack_bf162(f[0], f[1]), pack_bf162(f[2], f[3]),
+                           pack_bf162(f[4], f[5]), pack_bf162(f[6], f[7]));
+            else
+              st_shared_v4(row_addr + ((j ^ (lane & 7)) << 4), pack_half2(f[0], f[1]), pack_half2(f[2], f[3]),
+                           pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
-        const int col0 = tn * BN + c * 64;
-        if (lane == 0 && row0 < M && col0 < N) {
-          tma_store_2d(&tmC, buf, col0, row0);
+        const int col0 = tn * BN + c * CC;
+        if (lane == 0) {
+          // One bulk group per chunk, also for chunks that lie outside C (ragged N or M): the wait_read<1> above counts
+          // groups, and an uncounted chunk would let the chunk after it overwrite a buffer whose store is still reading.
+          if (row0 < M && col0 < N) tma_store_2d(&tmC, buf, col0, row0);
           tma_store_commit();
         }
       }
@@ -266,11 +283,11 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
                         const DeviceInfo& di, int tune) {
   CUtensorMap tmA, tmB, tmC;
   int rc;
-  if ((rc = make_tmap_2d_u16(&tmA, A, M, K, K, Cfg::BM_CTA, Cfg::BK, true))) return rc;
-  if (Cfg::B_MN) rc = make_tmap_2d_u16(&tmB, B, K, N, N, Cfg::BK, 64, true);
-  else rc = make_tmap_2d_u16(&tmB, B, N, K, K, Cfg::BN_CTA, Cfg::BK, true);
+  if ((rc = make_tmap_2d(&tmA, A, M, K, K, Cfg::BM_CTA, Cfg::BK, Cfg::ELEM))) return rc;
+  if (Cfg::B_MN) rc = make_tmap_2d(&tmB, B, K, N, N, Cfg::BK, Cfg::ROW_ELEMS, Cfg::ELEM);
+  else rc = make_tmap_2d(&tmB, B, N, K, K, Cfg::BN_CTA, Cfg::BK, Cfg::ELEM);
   if (rc) return rc;
-  if ((rc = make_tmap_2d_u16(&tmC, C, M, N, N, 32, 64, true))) return rc;
+  if ((rc = make_tmap_2d(&tmC, C, M, N, N, 32, Cfg::ROW_ELEMS, Cfg::ELEM))) return rc;
 
   const int tiles_m = int((M + Cfg::BM - 1) / Cfg::BM);
   const int tiles_n = int((N + Cfg::BN - 1) / Cfg::BN);
@@ -312,15 +329,17 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
 
 }  // namespace b200k
 
-extern "C" int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk,
-                               int variant, void* stream) {
-  using namespace b200k;
-  if (!A || !B || !C) return set_error(B200K_EARG, "b200k_hgemm_f16: null pointer");
+namespace b200k {
+template <int DT>
+static int gemm_dispatch(const char* who, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,
+                         int b_is_nk, int variant, void* stream) {
+  constexpr int PACK = (DT == 2) ? 4 : 8;  // elements per 16 bytes
+  if (!A || !B || !C) return set_error(B200K_EARG, "%s: null pointer", who);
   if (M < 1 || N < 1 || K < 1 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
-    return set_error(B200K_ESHAPE, "b200k_hgemm_f16: M,N,K must be in [1, 2^31) (got %lld,%lld,%lld)", (long long)M,
-                     (long long)N, (long long)K);
-  if ((K % 8) || (N % 8))
-    return set_error(B200K_ESHAPE, "b200k_hgemm_f16: K and N must be multiples of 8 (16-byte rows), got K=%lld N=%lld",
+    return set_error(B200K_ESHAPE, "%s: M,N,K must be in [1, 2^31) (got %lld,%lld,%lld)", who, (long long)M, (long long)N,
+                     (long long)K);
+  if ((K % PACK) || (N % PACK))
+    return set_error(B200K_ESHAPE, "%s: K and N must be multiples of %d (16-byte rows), got K=%lld N=%lld", who, PACK,
                      (long long)K, (long long)N);
   DeviceInfo di;
   int rc = get_device_info(&di);
@@ -335,18 +354,53 @@ extern "C" int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M,
     const int64_t t256 = ((M + 255) / 256) * ((N + 255) / 256);
     variant = (t256 * 4 >= di.sm_count) ? B200K_HGEMM_2CTA_256x256 : B200K_HGEMM_1CTA_128x256;
   }
+  // A 32-bit MN-major operand needs the 128B-swizzle-with-32B-atoms shared-memory layout, which this kernel does not
+  // stage: the TF32 build exists for K-major B only and b200k_gemm transposes an [K,N] B into its workspace first.
+  constexpr bool NN_OK = (DT != 2);
   const bool nn = (b_is_nk == 0);
+  if (nn && !NN_OK) return set_error(B200K_EARG, "%s: internal: MN-major B is not built for fp32 operands", who);
   switch (variant) {
     case B200K_HGEMM_1CTA_128x256:
-      return nn ? launch_hgemm<GemmCfg<1, 256, true, 4>>(A, B, C, M, N, K, s, di, tune)
-                : launch_hgemm<GemmCfg<1, 256, false, 4>>(A, B, C, M, N, K, s, di, tune);
+      return nn ? launch_hgemm<GemmCfg<1, 256, NN_OK, 4, DT>>(A, B, C, M, N, K, s, di, tune)
+                : launch_hgemm<GemmCfg<1, 256, false, 4, DT>>(A, B, C, M, N, K, s, di, tune);
     case B200K_HGEMM_2CTA_256x256:
-      return nn ? launch_hgemm<GemmCfg<2, 256, true, 6>>(A, B, C, M, N, K, s, di, tune)
-                : launch_hgemm<GemmCfg<2, 256, false, 6>>(A, B, C, M, N, K, s, di, tune);
+      return nn ? launch_hgemm<GemmCfg<2, 256, NN_OK, 6, DT>>(A, B, C, M, N, K, s, di, tune)
+                : launch_hgemm<GemmCfg<2, 256, false, 6, DT>>(A, B, C, M, N, K, s, di, tune);
     case B200K_HGEMM_2CTA_256x128:
-      return nn ? launch_hgemm<GemmCfg<2, 128, true, 8>>(A, B, C, M, N, K, s, di, tune)
-                : launch_hgemm<GemmCfg<2, 128, false, 8>>(A, B, C, M, N, K, s, di, tune);
+      return nn ? launch_hgemm<GemmCfg<2, 128, NN_OK, 8, DT>>(A, B, C, M, N, K, s, di, tune)
+                : launch_hgemm<GemmCfg<2, 128, false, 8, DT>>(A, B, C, M, N, K, s, di, tune);
     default:
-      return set_error(B200K_EARG, "b200k_hgemm_f16: unknown variant %d", variant);
+      return set_error(B200K_EARG, "%s: unknown variant %d", who, variant);
+  }
+}
+}  // namespace b200k
+
+extern "C" int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk,
+                               int variant, void* stream) {
+  return b200k::gemm_dispatch<0>("b200k_hgemm_f16", A, B, C, M, N, K, b_is_nk, variant, stream);
+}
+
+extern "C" size_t b200k_gemm_workspace_bytes(int64_t N, int64_t K, int dtype, int b_is_nk) {
+  return (dtype == B200K_F32 && !b_is_nk && N > 0 && K > 0) ? size_t(N) * size_t(K) * 4 : 0;
+}
+
+extern "C" int b200k_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk, int dtype,
+                          int variant, void* workspace, size_t workspace_bytes, void* stream) {
+  switch (dtype) {
+    case B200K_F16: return b200k::gemm_dispatch<0>("b200k_gemm(f16)", A, B, C, M, N, K, b_is_nk, variant, stream);
+    case B200K_BF16: return b200k::gemm_dispatch<1>("b200k_gemm(bf16)", A, B, C, M, N, K, b_is_nk, variant, stream);
+    case B200K_F32: {
+      if (b_is_nk) return b200k::gemm_dispatch<2>("b200k_gemm(tf32)", A, B, C, M, N, K, 1, variant, stream);
+      // NN: B [K,N] -> B^T [N,K] in the workspace (one extra read + write of B), then the K-major kernel
+      const size_t need = b200k_gemm_workspace_bytes(N, K, dtype, 0);
+      if (!workspace || workspace_bytes < need)
+        return b200k::set_error(B200K_EARG, "b200k_gemm(tf32, NN): needs a workspace of %llu bytes (b200k_gemm_workspace_bytes)",
+                                (unsigned long long)need);
+      if (!A || !B || !C) return b200k::set_error(B200K_EARG, "b200k_gemm(tf32): null pointer");
+      int rc = b200k_mat_transpose_f32(B, workspace, K, N, stream);
+      if (rc) return rc;
+      return b200k::gemm_dispatch<2>("b200k_gemm(tf32)", A, workspace, C, M, N, K, 1, variant, stream);
+    }
+    default: return b200k::set_error(B200K_EDTYPE, "b200k_gemm: dtype %d not supported (f16, bf16, f32-as-tf32)", dtype);
   }
 }

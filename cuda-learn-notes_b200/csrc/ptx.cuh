@@ -231,10 +231,28 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]       (kind::f16: fp16/bf16 operands, f32 or f16 accumulate)
-template <int CTA_GROUP>
+template <int CTA_GROUP, bool TF32 = false>
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
-  if constexpr (CTA_GROUP == 1)
+  if constexpr (TF32 && CTA_GROUP == 1)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else if constexpr (TF32)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else if constexpr (CTA_GROUP == 1)
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -370,10 +388,22 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n, bo
          ((m >> 4) << 24);
 }
 
+// Same descriptor with the operand format spelled out: 0 = f16, 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32); fp32
+// accumulation.
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t m, uint32_t n, int fmt, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (uint32_t(fmt) << 7) | (uint32_t(fmt) << 10) | (uint32_t(a_mn_major ? 1 : 0) << 15) |
+         (uint32_t(b_mn_major ? 1 : 0) << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
 // ---------------------------------------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf162(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");

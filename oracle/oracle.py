@@ -226,3 +226,14 @@ def mat_transpose(x):
 def gemv(a, x):
     """y = a @ x (sgemv.cu:L32-52, hgemv.cu:L34-52) in float64."""
     return a.detach().cpu().double() @ x.detach().cpu().double().reshape(-1, 1)
+
+
+def gemm_tf32_bound(a, b):
+    """C = A @ B in float64 together with a rigorous elementwise bound on what a TF32 tensor-core product may return:
+    the tensor core ignores the low 13 mantissa bits of each fp32 operand (relative error < 2^-10 per operand, so
+    < 2^-9 + 2^-20 per product) and accumulates in fp32 (sgemm_wmma_tf32_stage.cu:L25-60 rounds with
+    wmma::__float_to_tf32 instead, which is tighter).  Returns (exact, bound)."""
+    ad, bd = a.detach().cpu().double(), b.detach().cpu().double()
+    exact = ad @ bd
+    mag = ad.abs() @ bd.abs()
+    return exact, mag * (2.0 ** -9 + 2.0 ** -18)

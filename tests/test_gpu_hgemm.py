@@ -105,3 +105,75 @@ def test_hgemm_16384_smoke_and_stream():
     idx = torch.randint(0, n, (128, 2), device="cuda")
     want = (a[idx[:, 0]].double() * b[:, idx[:, 1]].t().double()).sum(-1)
     assert torch.allclose(c[idx[:, 0], idx[:, 1]].double(), want, **_tol(n))
+
+
+@pytest.mark.parametrize("tn", [False, True])
+@pytest.mark.parametrize("shape", [(256, 256, 256), (1024, 512, 768), (300, 264, 200), (2048, 2048, 2048)])
+def test_bf16_gemm_vs_float64(shape, tn):
+    """bf16 build of the GEMM kernel: fp32 accumulation, one rounding to bf16 (2^-9 relative)."""
+    from b200k import ops
+
+    M, N, K = shape
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = torch.randn(K, N, device="cuda").bfloat16()
+    c = torch.full((M, N), float("nan"), device="cuda").bfloat16()
+    bb = b.t().contiguous().t() if tn else b
+    ops.gemm(a, bb, c, tn=tn)
+    exact = a.double().cpu() @ b.double().cpu()
+    mag = a.double().abs().cpu() @ b.double().abs().cpu()
+    assert torch.isfinite(c).all()
+    assert ((c.double().cpu() - exact).abs() <= 2.0 ** -8 * exact.abs() + 1e-6 * mag + 1e-30).all()
+
+
+@pytest.mark.parametrize("tn", [False, True])
+@pytest.mark.parametrize("shape", [(256, 256, 256), (1024, 512, 768), (300, 260, 204), (2048, 2048, 2048)])
+def test_tf32_gemm_within_the_truncation_bound(shape, tn):
+    """TF32 build (fp32 in / out): every entry within the rigorous bound of 13 ignored mantissa bits per operand plus
+    fp32 accumulation, and on average far better (random signs cancel)."""
+    from b200k import ops
+
+    M, N, K = shape
+    torch.manual_seed(M * 3 + N + K)
+    a = torch.randn(M, K, device="cuda")
+    b = torch.randn(K, N, device="cuda")
+    c = torch.full((M, N), float("nan"), device="cuda")
+    bb = b.t().contiguous().t() if tn else b
+    ops.gemm(a, bb, c, tn=tn)
+    exact, bound = oracle.gemm_tf32_bound(a, b)
+    err = (c.double().cpu() - exact).abs()
+    assert torch.isfinite(c).all()
+    assert (err <= bound + 1e-6 * bound).all(), float((err / bound).max())
+    assert float(err.mean()) < 2e-3 * float(exact.abs().mean())
+
+
+def test_gemm_f16_entry_is_the_hgemm_kernel():
+    from b200k import ops
+
+    torch.manual_seed(3)
+    a = torch.randn(512, 256, dtype=torch.half, device="cuda")
+    b = torch.randn(256, 384, dtype=torch.half, device="cuda")
+    c0, c1 = torch.empty(512, 384, dtype=torch.half, device="cuda"), torch.empty(512, 384, dtype=torch.half, device="cuda")
+    ops.hgemm(a, b, c0)
+    ops.gemm(a, b, c1)
+    assert torch.equal(c0, c1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_ragged_n_epilogue_staging_buffers(dtype):
+    """Chunks of C outside a ragged N used to skip their bulk-group commit, so the next chunk could overwrite a staging
+    buffer whose TMA store was still reading (seen with the fp32 build at N = 384: the last valid 32-column chunk of
+    random row blocks was corrupted).  Short K makes the run epilogue-bound; repeated to give a race every chance."""
+    from b200k import ops
+
+    torch.manual_seed(7)
+    for (M, N, K) in ((2048, 264, 64), (1024, 384, 64), (4096, 296, 32), (512, 328, 128)):
+        a = torch.randn(M, K, device="cuda").to(dtype)
+        b = torch.randn(K, N, device="cuda").to(dtype)
+        want = a.double().cpu() @ b.double().cpu()
+        mag = a.double().abs().cpu() @ b.double().abs().cpu()
+        tol = 2.0 ** -9 if dtype == torch.float32 else 2.0 ** -7
+        for rep in range(10):
+            c = torch.full((M, N), float("nan"), device="cuda").to(dtype)
+            ops.gemm(a, b, c)
+            assert ((c.double().cpu() - want).abs() <= tol * mag + 1e-30).all(), (dtype, M, N, K, rep)
