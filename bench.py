@@ -368,7 +368,7 @@ def main():
                 "peak_source": peaks["source"] + "; burst cuBLAS bf16 figure (kernel timed back to back for ~20 ms)",
                 "kernel": "hgemm_tcgen05_kernel<2-CTA 256x256x64, 6 stages>",
                 "algorithmic_flops_per_launch": flops,
-                "traffic": 1.203e9, "traffic_source": "profiles/r01_hgemm_8192_ncu_summary.json (dram read+write per launch); "
+                "traffic": 1.275e9, "traffic_source": "profiles/r01_hgemm_8192_ncu_summary.json (dram read+write per launch); "
                 "algorithmic bytes 4.03e8"}
 
     if not args.quick:

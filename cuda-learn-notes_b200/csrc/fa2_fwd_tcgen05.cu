@@ -87,7 +87,7 @@ template <class Cfg, bool TRACE, int POLY, int NP>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int N,
-                       float scale_log2, unsigned long long* trace, int pingpong) {
+                       float scale_log2, unsigned long long* trace) {
   auto tr = [&](int role, int j, int ev) {
     if constexpr (TRACE) {
       if (blockIdx.x == 0 && blockIdx.y == 0 && j < kTraceIters)
@@ -360,10 +360,6 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t o_tmem = tmem_base + lane_base + (i ? Cfg::O_COL1 : Cfg::O_COL0);
     float m_ref = -INFINITY;  // reference max, in log2-scaled units
     float l = 0.f;
-    // Optional turn-taking of the exp2 phase between the two warpgroups (named barriers 1 and 2, 256 threads): while
-    // one warpgroup owns the MUFU pipe the other does its load / max / store / handshake work, instead of both
-    // drifting into lock-step and leaving the MUFU idle during those phases.
-    if (pingpong && i == 1) named_bar_arrive(1, 256);
     for (int j = 0; j < T; ++j) {
       mbar_wait(bar_s_full + 8 * i, j & 1);
       const bool tw = TRACE && lane == 0 && q == 0;  // one thread per warpgroup writes the trace
@@ -421,14 +417,12 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tmem_wait_st();
         }
       }
-      if (pingpong) named_bar_sync(1 + i, 256);
       if (tw) tr(1 + i, j, 2);
       // P = exp2(s * scale_log2 - m_ref), row sum in fp32, P packed to fp16 pairs in place
       // processed in blocks of 16 with packed fp32x2 arithmetic (FFMA2 / FADD2: one issue slot per two elements);
       // all FFMA2s of a block, then its MUFU.EX2s, then sums / packs, so 16 independent exponentials are in flight
       float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-      float neg_m = -m_ref;
-      if (pingpong) asm volatile("" : "+f"(neg_m));  // pins the exponentials behind the turn-taking barrier
+      const float neg_m = -m_ref;
       const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(neg_m, neg_m);
       constexpr int PIECE = BC / NP;  // keys per piece of P
 #pragma unroll
@@ -472,7 +466,6 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
       }
       l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
-      if (pingpong) named_bar_arrive(2 - i, 256);
       if (tw) tr(1 + i, j, 6);
     }
     // ---- epilogue: O_i / l -> fp16 -> swizzled smem (reusing this tile's Q buffer) -> TMA store
@@ -516,8 +509,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
 template <class Cfg>
 static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N, float scale,
-                      cudaStream_t stream, const DeviceInfo& di, int np = 0, bool trace = false, int pingpong = 0,
-                      int poly = 0) {
+                      cudaStream_t stream, const DeviceInfo& di, int np = 0, bool trace = false, int poly = 0) {
   constexpr int D = Cfg::D;
   const uint64_t BH = uint64_t(B) * uint64_t(H);
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -537,7 +529,7 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
   dim3 grid(unsigned((N + 255) / 256), unsigned(BH));
   const float scale_log2 = scale * 1.4426950408889634f;
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, int, float,
-                        unsigned long long*, int);
+                        unsigned long long*);
   Kern kern;
   unsigned long long* tbuf = nullptr;
   // Experiment / debug instantiations (piece counts, cycle trace, higher polynomial fractions) only exist for the two
@@ -570,7 +562,7 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
     if (done.insert({reinterpret_cast<const void*>(kern), di.device}).second)
       B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, tbuf, pingpong);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, tbuf);
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;
 }
@@ -583,8 +575,6 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
   const bool trace = (variant & 0x100) != 0;  // debugging: cycle trace of CTA (0,0), see b200k_debug_set_trace
   // Experiment switches (round-robin measurements on one B200, profiles/r01_fa2_variants.txt and r01_fa2_*.log;
   // TFLOP/s at (4,48,8192,64) unless noted):
-  //   0x200        exp2-phase turn-taking between the two softmax warpgroups (named barriers): 744 vs 812 without ->
-  //                off.  A turn also holds the MUFU pipe through the P store / hand-over of the warpgroup that owns it.
   //   0x400        D = 128 only: P aliases S (S0 S1 O0 O1) instead of the shared S buffer: 1122 vs 1223.
   //   bits 12-13   P handed to the MMA thread in 1 / 2 / 4 pieces per KV tile.  D = 64: 731 / 817 / 761 -> 2;
   //                D = 128 (shared S): 1267 / 1209 / 1202 -> 1.
@@ -593,10 +583,11 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
   //                D = 128: 1144 / 1209 / 1155; D = 32: 414 / 426; D = 96: 912 / 920.  Default 1 (value 0), 7 = none.
   //   0x800        older spelling of "3 of 8".
   //   0x20000      D = 64 only: one shared S buffer as for D = 128 (forced ping-pong of the two tiles): 2 % slower.
-  // Tried and removed (kept out of the build): two threads per query row (16 softmax warps, 96 registers): D = 64
+  // Tried and removed (kept out of the build): exp2-phase turn-taking between the two softmax warpgroups through named
+  // barriers (744 vs 812: a turn also holds the MUFU pipe through the P store / hand-over of the warpgroup that owns
+  // it); two threads per query row (16 softmax warps, 96 registers): D = 64
   // 829 vs 799, D = 128 1217 vs 1211 - within noise for twice the softmax code; an event-driven MMA issue loop
   // (non-blocking mbarrier probes, whichever tile is ready): slower, the single issuing thread becomes the bottleneck.
-  const int pingpong = (variant & 0x200) ? 1 : 0;
   const int poly_sel = (variant >> 14) & 7;
   const int poly = poly_sel == 7 ? 0 : (poly_sel ? min(4, poly_sel) : ((variant & 0x800) ? 3 : 1));
   const int np_sel = (variant >> 12) & 3;  // 0 default, 1 -> 1 piece, 2 -> 2 pieces, 3 -> 4 pieces
@@ -615,24 +606,24 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (v_is_dn) {
     switch (D) {
-      case 32: return launch_fa2<Fa2Cfg<32, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
-      case 64: return launch_fa2<Fa2Cfg<64, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
-      case 96: return launch_fa2<Fa2Cfg<96, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
-      default: return launch_fa2<Fa2Cfg<128, 128, 2, true, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
+      case 32: return launch_fa2<Fa2Cfg<32, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
+      case 64: return launch_fa2<Fa2Cfg<64, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
+      case 96: return launch_fa2<Fa2Cfg<96, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
+      default: return launch_fa2<Fa2Cfg<128, 128, 2, true, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
     }
   }
   switch (D) {
-    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
+    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
     case 64:
       if (variant & 0x20000)  // one shared S buffer (forced ping-pong of the two tiles) as for D = 128: 2 % slower here
-        return launch_fa2<Fa2Cfg<64, 128, 4, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
-      return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
-    case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, pingpong, poly);
+        return launch_fa2<Fa2Cfg<64, 128, 4, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly);
+      return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly);
+    case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
     default:
       // 0x400: the older layout for D = 128 (P aliases S, S0 S1 O0 O1) instead of the shared S buffer
       if (variant & 0x400)
-        return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
-      return launch_fa2<Fa2Cfg<128, 128, 2, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, pingpong, poly);
+        return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly);
+      return launch_fa2<Fa2Cfg<128, 128, 2, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly);
   }
 }
 

@@ -70,10 +70,10 @@ def test_large_logits_exercise_lazy_rescale():
     assert torch.allclose(_run(q, k, v).cpu().float(), oracle.attention(q, k, v).float(), **TOL)
 
 
-@pytest.mark.parametrize("variant", [0x1C000, 0x8000, 0x10000, 0x1000, 0x3000, 0x200])
+@pytest.mark.parametrize("variant", [0x1C000, 0x8000, 0x10000, 0x1000, 0x2000, 0x3000, 0x400, 0x20000])
 @pytest.mark.parametrize("D", [64, 128])
 def test_fa2_experiment_builds_agree_with_oracle(D, variant):
-    """Every selectable build of the FA-2 kernel (no / more polynomial exponentials, 1 / 4 P pieces, turn-taking)
+    """Every selectable build of the FA-2 kernel (no / more polynomial exponentials, 1 / 2 / 4 P pieces, the aliased-P and shared-S TMEM layouts)
     must give the same answer as the default one; also covers very negative scores (masked-like keys) on the
     polynomial exp2 path, which has to flush them to zero like MUFU.EX2 does."""
     from b200k import ops
