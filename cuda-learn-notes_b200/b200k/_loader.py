@@ -57,8 +57,7 @@ _SIGS = {
     "b200k_last_error": (c_char_p, []),
     "b200k_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "b200k_hgemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
-    "b200k_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "b200k_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "b200k_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "b200k_fa2_fwd_f16": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_float, c_int, c_int, c_void_p]),
     "b200k_ffpa_fwd_f16": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_float, c_int, c_void_p]),
     "b200k_elementwise_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),

@@ -98,19 +98,6 @@ def hgemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, tn: bool = False, v
                                      _stream(a)))
 
 
-_gemm_ws_cache: dict = {}
-
-
-def _gemm_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    """Scratch for the fp32 NN path (B is transposed once per call); grown on demand, one buffer per device."""
-    key = (dev.type, dev.index)
-    ws = _gemm_ws_cache.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _gemm_ws_cache[key] = ws
-    return ws
-
-
 def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, tn: bool = False, variant: int = L.HGEMM_AUTO) -> None:
     """c = a @ B for fp16, bf16 (fp32 accumulation) or fp32 operands (TF32 tensor-core product, fp32 accumulation and
     output); same layouts as :func:`hgemm`."""
@@ -127,10 +114,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, tn: bool = False, va
     else:
         _check_cuda_contig(a, b, c)
     with _DeviceGuard(a):
-        need = int(_lib.b200k_gemm_workspace_bytes(N, K, _DTYPE_ENUM[a.dtype], 1 if tn else 0))
-        ws = _gemm_workspace(a.device, need) if need else None
         L.check(_lib.b200k_gemm(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, 1 if tn else 0, _DTYPE_ENUM[a.dtype],
-                                variant, ws.data_ptr() if ws is not None else None, need, _stream(a)))
+                                variant, _stream(a)))
 
 
 # ------------------------------------------------------------------------------------------------ attention

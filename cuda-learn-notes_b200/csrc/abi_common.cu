@@ -83,7 +83,7 @@ int make_tmap_2d_u16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 }
 
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows,
-                 uint32_t box_cols, int elem_bytes) {
+                 uint32_t box_cols, int elem_bytes, bool atom32) {
   if (elem_bytes == 2) return make_tmap_2d_u16(out, base, rows, cols, pitch_elems, box_rows, box_cols, true);
   EncodeTiledFn fn;
   int rc = get_encode_fn(&fn);
@@ -96,8 +96,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(B200K_ECUDA, "cuTensorMapEncodeTiled(2d f32 rows=%llu cols=%llu box=%ux%u) failed with CUresult %d",
                      (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols, (int)r);

@@ -36,7 +36,7 @@ int make_tmap_2d_u16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
                      uint32_t box_rows, uint32_t box_cols, bool swizzle128);
 // same, for 2-byte (f16 / bf16) or 4-byte (fp32) elements; always SWIZZLE_128B
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows,
-                 uint32_t box_cols, int elem_bytes);
+                 uint32_t box_cols, int elem_bytes, bool atom32 = false);
 // 3-D variant: [d2, d1, d0] with d0 contiguous, strides in elements; swizzle_bytes in {0, 32, 64, 128}.
 int make_tmap_3d_u16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint64_t stride2,
                      uint64_t stride1, uint32_t box2, uint32_t box1, uint32_t box0, int swizzle_bytes);

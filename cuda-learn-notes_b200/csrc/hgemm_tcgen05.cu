@@ -172,7 +172,12 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr uint64_t a_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);
       // B (TN): same K-major layout.  B (NN): MN-major, one 128 B row = 64 (32 for tf32) N-elements, 8 K-rows per
       // 1024 B atom (SBO), the next row-full of N-elements one TMA box (BK rows x 128 B) further (LBO).
-      constexpr uint64_t b_hi = B_MN ? make_smem_desc_hi(Cfg::BK * 128, 1024, kSwizzle128B) : make_smem_desc_hi(16, 1024, kSwizzle128B);
+      // A 32-bit MN-major operand uses the "128B swizzle, 32-byte atoms" layout (UMMA layout type 1, TMA
+      // SWIZZLE_128B_ATOM_32B): atoms are 4 K-rows tall, so the two atoms of one K = 8 step are SBO = 512 B apart.
+      constexpr bool MN32 = B_MN && Cfg::DT == 2;
+      constexpr uint64_t b_hi = MN32   ? make_smem_desc_hi(Cfg::BK * 128, 512, 1)
+                                : B_MN ? make_smem_desc_hi(Cfg::BK * 128, 1024, kSwizzle128B)
+                                       : make_smem_desc_hi(16, 1024, kSwizzle128B);
       constexpr uint32_t b_kstep = B_MN ? uint32_t(Cfg::UMMA_K) * 128u : 32u;  // bytes per UMMA K step
       int stage = 0;
       uint32_t phase = 0;
@@ -284,7 +289,7 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   CUtensorMap tmA, tmB, tmC;
   int rc;
   if ((rc = make_tmap_2d(&tmA, A, M, K, K, Cfg::BM_CTA, Cfg::BK, Cfg::ELEM))) return rc;
-  if (Cfg::B_MN) rc = make_tmap_2d(&tmB, B, K, N, N, Cfg::BK, Cfg::ROW_ELEMS, Cfg::ELEM);
+  if (Cfg::B_MN) rc = make_tmap_2d(&tmB, B, K, N, N, Cfg::BK, Cfg::ROW_ELEMS, Cfg::ELEM, /*atom32=*/Cfg::DT == 2);
   else rc = make_tmap_2d(&tmB, B, N, K, K, Cfg::BN_CTA, Cfg::BK, Cfg::ELEM);
   if (rc) return rc;
   if ((rc = make_tmap_2d(&tmC, C, M, N, N, 32, Cfg::ROW_ELEMS, Cfg::ELEM))) return rc;
@@ -354,20 +359,16 @@ static int gemm_dispatch(const char* who, const void* A, const void* B, void* C,
     const int64_t t256 = ((M + 255) / 256) * ((N + 255) / 256);
     variant = (t256 * 4 >= di.sm_count) ? B200K_HGEMM_2CTA_256x256 : B200K_HGEMM_1CTA_128x256;
   }
-  // A 32-bit MN-major operand needs the 128B-swizzle-with-32B-atoms shared-memory layout, which this kernel does not
-  // stage: the TF32 build exists for K-major B only and b200k_gemm transposes an [K,N] B into its workspace first.
-  constexpr bool NN_OK = (DT != 2);
   const bool nn = (b_is_nk == 0);
-  if (nn && !NN_OK) return set_error(B200K_EARG, "%s: internal: MN-major B is not built for fp32 operands", who);
   switch (variant) {
     case B200K_HGEMM_1CTA_128x256:
-      return nn ? launch_hgemm<GemmCfg<1, 256, NN_OK, 4, DT>>(A, B, C, M, N, K, s, di, tune)
+      return nn ? launch_hgemm<GemmCfg<1, 256, true, 4, DT>>(A, B, C, M, N, K, s, di, tune)
                 : launch_hgemm<GemmCfg<1, 256, false, 4, DT>>(A, B, C, M, N, K, s, di, tune);
     case B200K_HGEMM_2CTA_256x256:
-      return nn ? launch_hgemm<GemmCfg<2, 256, NN_OK, 6, DT>>(A, B, C, M, N, K, s, di, tune)
+      return nn ? launch_hgemm<GemmCfg<2, 256, true, 6, DT>>(A, B, C, M, N, K, s, di, tune)
                 : launch_hgemm<GemmCfg<2, 256, false, 6, DT>>(A, B, C, M, N, K, s, di, tune);
     case B200K_HGEMM_2CTA_256x128:
-      return nn ? launch_hgemm<GemmCfg<2, 128, NN_OK, 8, DT>>(A, B, C, M, N, K, s, di, tune)
+      return nn ? launch_hgemm<GemmCfg<2, 128, true, 8, DT>>(A, B, C, M, N, K, s, di, tune)
                 : launch_hgemm<GemmCfg<2, 128, false, 8, DT>>(A, B, C, M, N, K, s, di, tune);
     default:
       return set_error(B200K_EARG, "%s: unknown variant %d", who, variant);
@@ -380,27 +381,12 @@ extern "C" int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M,
   return b200k::gemm_dispatch<0>("b200k_hgemm_f16", A, B, C, M, N, K, b_is_nk, variant, stream);
 }
 
-extern "C" size_t b200k_gemm_workspace_bytes(int64_t N, int64_t K, int dtype, int b_is_nk) {
-  return (dtype == B200K_F32 && !b_is_nk && N > 0 && K > 0) ? size_t(N) * size_t(K) * 4 : 0;
-}
-
 extern "C" int b200k_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk, int dtype,
-                          int variant, void* workspace, size_t workspace_bytes, void* stream) {
+                          int variant, void* stream) {
   switch (dtype) {
     case B200K_F16: return b200k::gemm_dispatch<0>("b200k_gemm(f16)", A, B, C, M, N, K, b_is_nk, variant, stream);
     case B200K_BF16: return b200k::gemm_dispatch<1>("b200k_gemm(bf16)", A, B, C, M, N, K, b_is_nk, variant, stream);
-    case B200K_F32: {
-      if (b_is_nk) return b200k::gemm_dispatch<2>("b200k_gemm(tf32)", A, B, C, M, N, K, 1, variant, stream);
-      // NN: B [K,N] -> B^T [N,K] in the workspace (one extra read + write of B), then the K-major kernel
-      const size_t need = b200k_gemm_workspace_bytes(N, K, dtype, 0);
-      if (!workspace || workspace_bytes < need)
-        return b200k::set_error(B200K_EARG, "b200k_gemm(tf32, NN): needs a workspace of %llu bytes (b200k_gemm_workspace_bytes)",
-                                (unsigned long long)need);
-      if (!A || !B || !C) return b200k::set_error(B200K_EARG, "b200k_gemm(tf32): null pointer");
-      int rc = b200k_mat_transpose_f32(B, workspace, K, N, stream);
-      if (rc) return rc;
-      return b200k::gemm_dispatch<2>("b200k_gemm(tf32)", A, workspace, C, M, N, K, 1, variant, stream);
-    }
+    case B200K_F32: return b200k::gemm_dispatch<2>("b200k_gemm(tf32)", A, B, C, M, N, K, b_is_nk, variant, stream);
     default: return b200k::set_error(B200K_EDTYPE, "b200k_gemm: dtype %d not supported (f16, bf16, f32-as-tf32)", dtype);
   }
 }

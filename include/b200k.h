@@ -61,12 +61,10 @@ int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N,
  * B200K_BF16 (bf16 in / bf16 out, fp32 accumulation), or B200K_F32 = TF32 tensor-core product of fp32 matrices with
  * fp32 output (tcgen05.mma kind::tf32: the operands' low 13 mantissa bits are ignored by the tensor core, fp32
  * accumulation) - the B200 counterpart of kernels/sgemm/sgemm_wmma_tf32_stage.cu:L25-420 (sgemm_wmma_m16n16k8_*).
- * K and N must be multiples of 8 (16-bit types) or 4 (fp32).  fp32 with b_is_nk = 0 transposes B into `workspace` first
- * (>= b200k_gemm_workspace_bytes(N, K, dtype, b_is_nk) bytes, device memory; may be NULL otherwise): a 32-bit
- * MN-major operand needs a shared-memory layout (128B swizzle, 32B atoms) this kernel does not stage yet. */
-size_t b200k_gemm_workspace_bytes(int64_t N, int64_t K, int dtype, int b_is_nk);
+ * K and N must be multiples of 8 (16-bit types) or 4 (fp32).  An fp32 [K,N] B is read as an MN-major operand through the
+ * "128B swizzle with 32-byte atoms" shared-memory layout (TMA SWIZZLE_128B_ATOM_32B, UMMA layout type 1). */
 int b200k_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk, int dtype, int variant,
-               void* workspace, size_t workspace_bytes, void* stream);
+               void* stream);
 
 /* ------------------------------------------------------------------------------------------------ attention
  * O = softmax(Q K^T * scale) V, non-causal, Q/K/V/O [B,H,N,D] fp16 contiguous (V optionally [B,H,D,N]).

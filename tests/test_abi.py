@@ -49,12 +49,3 @@ def test_no_gpu_means_loud_failure_not_fallback():
     with pytest.raises(L.B200KError):
         L.device_info()
 
-
-def test_gemm_workspace_size_is_a_pure_host_query():
-    """b200k_gemm_workspace_bytes needs no GPU: only the fp32 [K,N]-B path transposes B into a workspace."""
-    from b200k import _loader as L
-
-    assert L.lib.b200k_gemm_workspace_bytes(384, 256, L.F32, 0) == 384 * 256 * 4
-    assert L.lib.b200k_gemm_workspace_bytes(384, 256, L.F32, 1) == 0
-    assert L.lib.b200k_gemm_workspace_bytes(384, 256, L.F16, 0) == 0
-    assert L.lib.b200k_gemm_workspace_bytes(384, 256, L.BF16, 0) == 0
