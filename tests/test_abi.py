@@ -36,6 +36,17 @@ def test_argument_validation_happens_before_cuda():
     assert lib.b200k_rope_f32(one, one, 4, 7, 1, None) == L.ESHAPE
     assert lib.b200k_softmax(one, one, 4, 8, L.F32, 9, None, None) == L.EARG
     assert lib.b200k_embedding(one, one, one, 4, 4, 4, L.I8, None) == L.EDTYPE
+    # generic GEMM entry: fp32 rows must be 16-byte multiples too (4 elements), unknown dtypes are refused
+    assert lib.b200k_gemm(one, one, one, 8, 8, 6, 0, L.F32, 0, None) == L.ESHAPE
+    assert b"multiples of 4" in lib.b200k_last_error()
+    assert lib.b200k_gemm(one, one, one, 8, 8, 4, 0, L.BF16, 0, None) == L.ESHAPE
+    assert lib.b200k_gemm(one, one, one, 8, 8, 8, 0, L.I8, 0, None) == L.EDTYPE
+    assert lib.b200k_gemm(None, one, one, 8, 8, 8, 1, L.F32, 0, None) == L.EARG
+    # second set of support kernels
+    assert lib.b200k_layer_norm(one, one, 0, 8, 1.0, 0.0, 1e-5, L.F32, 1, None) == L.ESHAPE
+    assert lib.b200k_mat_transpose_f32(one, None, 4, 4, None) == L.EARG
+    assert lib.b200k_gemv(one, one, one, 4, 0, L.F32, None) == L.ESHAPE
+    assert lib.b200k_dot_prod(one, one, None, 4, L.F32, one, None) == L.EARG
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

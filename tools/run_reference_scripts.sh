@@ -14,9 +14,5 @@ for op in elementwise/elementwise.py softmax/softmax.py rms-norm/rms_norm.py rop
   n=$(basename $op .py)
   timeout 300 python -m b200k.run_ref_script $R/kernels/$op > $OUT/$n.log 2>&1; tail -2 $OUT/$n.log
 done
-# second set of support kernels: the scripts print their own kernels next to the torch comparator
-for op in relu/relu.py sigmoid/sigmoid.py gelu/gelu.py swish/swish.py elu/elu.py hardswish/hardswish.py hardshrink/hardshrink.py \
-          layer-norm/layer_norm.py dot-product/dot_product.py mat-transpose/mat_transpose.py sgemv/sgemv.py hgemv/hgemv.py; do
-  n=$(basename $op .py)
-  timeout 300 python -m b200k.run_ref_script $R/kernels/$op > $OUT/$n.log 2>&1; echo "$n rc=$?"; tail -2 $OUT/$n.log
-done
+# second set of support kernels
+bash $ROOT/tools/run_reference_scripts_set2.sh
