@@ -460,6 +460,50 @@ def main():
         out["ffpa"] = {"cfg4_b1_h32_n4096_d512": ffpa}
         torch.cuda.empty_cache()
 
+        # -------------------------------------------------------------- the widened rows, N = 1 only
+        if world == 1:
+            try:
+                gd = {}
+                for dt, nm in ((torch.bfloat16, "bf16"), (torch.float32, "tf32")):
+                    A = torch.randn(n, n, device=dev).to(dt)
+                    Bm = torch.randn(n, n, device=dev).to(dt)
+                    C = torch.empty(n, n, device=dev).to(dt)
+                    t_o = cuda_time(lambda: ops.gemm(A, Bm, C), 10, 3)
+                    launches += 13
+                    prev = torch.backends.cuda.matmul.allow_tf32
+                    torch.backends.cuda.matmul.allow_tf32 = True
+                    t_c = cuda_time(lambda: torch.matmul(A, Bm, out=C), 10, 3)
+                    torch.backends.cuda.matmul.allow_tf32 = prev
+                    gd[nm + "_8192"] = {"tflops": flops / t_o * 1e-9, "cublas_tflops": flops / t_c * 1e-9}
+                    del A, Bm, C
+                out["gemm_dtypes"] = gd
+            except Exception as e:  # noqa
+                out["gemm_dtypes"] = {"error": repr(e)[:200]}
+            try:
+                hbm = peaks.get("hbm_gbs")
+                ne = 64 * 1024 * 1024
+                xa, xb = torch.randn(ne, device=dev), torch.randn(ne, device=dev)
+                xc = torch.empty_like(xa)
+                xr = torch.randn(16384, 8192, dtype=torch.half, device=dev)
+                yr = torch.empty_like(xr)
+                sup = {}
+                for nm, fn, nbytes in (
+                        ("elementwise_add_f32", lambda: ops.elementwise_add(xa, xb, xc), 3 * ne * 4),
+                        ("block_all_reduce_sum_f32", lambda: ops.block_all_reduce_sum(xa), ne * 4),
+                        ("safe_softmax_f16_h8192", lambda: ops.softmax(xr, yr, ops.SOFTMAX_SAFE), 2 * xr.numel() * 2),
+                        ("rms_norm_f16_k8192", lambda: ops.rms_norm(xr, yr, 1.0), 2 * xr.numel() * 2),
+                        ("layer_norm_f16_k8192", lambda: ops.layer_norm(xr, yr, 1.0, 0.0), 2 * xr.numel() * 2),
+                        ("gelu_f32", lambda: ops.activation(xa, xc, "gelu"), 2 * ne * 4),
+                        ("dot_prod_f32", lambda: ops.dot_prod(xa, xb), 2 * ne * 4)):
+                    t_s = cuda_time(fn, 10, 3)
+                    launches += 13
+                    sup[nm] = {"gbps": nbytes / t_s * 1e-6, "frac_of_measured_hbm_peak": (nbytes / t_s * 1e-6 / hbm) if hbm else None}
+                out["support_hbm"] = sup
+                del xa, xb, xc, xr, yr
+            except Exception as e:  # noqa
+                out["support_hbm"] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+
         # -------------------------------------------------------------- config #5: batch-sharded attention over the ranks
         if dist_on:
             import torch.distributed as dist
