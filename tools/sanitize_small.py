@@ -16,5 +16,21 @@ for D, fn in ((64, ops.fa2_fwd), (128, ops.fa2_fwd), (96, ops.fa2_fwd), (256, op
     fn(q, k, v, o)
 x = torch.randn(77, 1000, device="cuda"); y = torch.empty_like(x)
 ops.softmax(x, y, 2); ops.rms_norm(x, y, 1.0); ops.block_all_reduce_sum(x)
+# round-1 additions: bf16 / TF32 GEMM (incl. the fp32 MN-major operand and a ragged N), D = 512 pair kernel, second support set
+for dt in (torch.bfloat16, torch.float32):
+    A = torch.randn(300, 264, device="cuda").to(dt); Bm = torch.randn(264, 392, device="cuda").to(dt)
+    Cc = torch.empty(300, 392, device="cuda").to(dt)
+    ops.gemm(A, Bm, Cc)
+    ops.gemm(A, Bm.t().contiguous().t(), Cc, tn=True)
+q, k, v = [torch.randn(1, 1, 300, 512, dtype=torch.half, device="cuda") for _ in range(3)]
+o = torch.empty_like(q)
+ops.ffpa_fwd(q, k, v, o)
+xh = torch.randn(33, 1000, dtype=torch.half, device="cuda"); yh = torch.empty_like(xh)
+for op in ("relu", "sigmoid", "gelu", "swish", "elu", "hardswish", "hardshrink"):
+    ops.activation(x, y, op); ops.activation(xh.flatten()[1:], yh.flatten()[1:], op)
+ops.layer_norm(x, y, 1.0, 0.0); ops.layer_norm(xh, yh, 1.0, 0.0); ops.dot_prod(x, y)
+t = torch.empty(1000, 77, device="cuda"); ops.mat_transpose(x, t)
+gv = torch.randn(1000, 1, device="cuda"); gy = torch.empty(77, 1, device="cuda"); ops.gemv(x, gv, gy)
+ops.rope_f32(x, y, True); ops.rope_f32(x, y, False)
 torch.cuda.synchronize()
 print("sanitize run done")
