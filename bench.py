@@ -232,6 +232,143 @@ def ref_swizzle_stride(N):  # hgemm.py:L71-81
     return s if s >= 256 else 1
 
 
+# ---------------------------------------------------------------------------------------------------- config #5 sharded
+NVLINK_MEASURED_GBPS = 770.0   # B200_PROFILING.md: measured peer copy per direction per GPU (nominal 900)
+
+
+def bench_sharded_cfg5(world, rank, dev, barrier, dist_on, peaks, reps=5, warm=2):
+    """BASELINE config #5, FA-2 forward (32,64,8192,128), batch-sharded over `world` GPUs.
+    Rank 0 holds Q, K, V (12.9 GB packed).  Timed, max over ranks, CUDA events, `warm` untimed + `reps` timed passes each:
+      compute only (inputs already distributed), the three input distributions alone, and distribution + compute end to end.
+    Rank 0 also runs the WHOLE problem alone (the N = 1 point on this box) and every shard is compared bit for bit with
+    that result."""
+    from b200k import ops, sharded
+    B_, H_, N_, D_ = FA2_CFG5
+    fl = 4.0 * B_ * H_ * N_ * N_ * D_
+    shape = (B_, H_, N_, D_)
+    rec = {"workload": "fa2_fwd_b32_h64_n8192_d128 (BASELINE config #5)", "n_gpus": world, "scaling": "strong",
+           "algorithmic_flops": fl, "timing": "CUDA events, %d warm-up + %d timed passes, max over ranks" % (warm, reps)}
+    n_launch = 0
+
+    def timed(fn, r=reps, w=warm):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        ts = []
+        for _ in range(r):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if barrier:
+                barrier()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(max_over_ranks(e0.elapsed_time(e1), dist_on))
+        ts.sort()
+        return ts[len(ts) // 2], ts[0], ts[-1]
+
+    qkv = None
+    o_full = None
+    if rank == 0:
+        g = torch.Generator(device=dev).manual_seed(5)
+        qkv = torch.empty(3, B_, H_, N_, D_, dtype=torch.half, device=dev)
+        for t in range(3):
+            qkv[t].normal_(generator=g)
+        o_full = torch.empty(B_, H_, N_, D_, dtype=torch.half, device=dev)
+    # ---- the N = 1 point: rank 0 alone runs the whole problem as ONE call (2^31 elements per tensor)
+    t_n1 = [None]
+    if rank == 0:
+        for _ in range(warm):
+            ops.fa2_fwd(qkv[0], qkv[1], qkv[2], o_full)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            ops.fa2_fwd(qkv[0], qkv[1], qkv[2], o_full)
+        e1.record()
+        torch.cuda.synchronize()
+        t_n1[0] = e0.elapsed_time(e1) / 3
+        n_launch += warm + 3
+    if dist_on:
+        import torch.distributed as dist
+        dist.broadcast_object_list(t_n1, src=0)
+    t1 = t_n1[0]
+    rec["n1_whole_problem_ms"] = t1
+    rec["n1_tflops"] = fl / t1 * 1e-9
+    if not dist_on:
+        rec.update({"compute_ms": t1, "aggregate_tflops": fl / t1 * 1e-9, "aggregate_tflops_incl_distribution": fl / t1 * 1e-9,
+                    "efficiency_vs_n1": 1.0, "note": "N = 1: no distribution; the whole (32,64,8192,128) problem as one "
+                    "kernel launch on one GPU (16 GiB of tensors)"})
+        rec["_launches"] = n_launch
+        return rec
+
+    lo, hi = sharded.shard_bounds(B_, world, rank)
+    o = torch.empty(hi - lo, H_, N_, D_, dtype=torch.half, device=dev)
+    qkv_bytes = 3 * B_ * H_ * N_ * D_ * 2
+    modes = {}
+    keep = {}
+    for mode in sharded.MODES:
+        # distribution alone (the handles are waited for on the stream; the events bracket the transfer itself)
+        def dist_only(mode=mode):
+            sh = sharded.distribute_qkv(qkv, shape, dev, mode=mode, chunk_batches=1)
+            sh.wait_all()
+            keep["sh"] = sh
+        td, td_min, td_max = timed(dist_only)
+        sh = keep["sh"]
+        # compute alone on the distributed shard
+        tc, _, _ = timed(lambda: sharded.attention_on_shard(sh, out=o))
+        n_launch += (warm + reps) * max(1, len(sh.chunks))
+        ok = sharded.shards_equal_to(o, o_full, B_)
+        del sh
+        keep.clear()
+        # distribution + compute, what a caller of config #5 pays
+        def both(mode=mode):
+            sharded.sharded_attention(qkv, shape, dev, mode=mode, out=o, chunk_batches=1)
+        tb, tb_min, tb_max = timed(both)
+        n_launch += (warm + reps) * (1 if mode != "pipelined" else (hi - lo))
+        ok2 = sharded.shards_equal_to(o, o_full, B_)
+        sent = qkv_bytes if mode == "broadcast" else qkv_bytes * (world - 1) / world
+        recv = qkv_bytes if mode == "broadcast" else qkv_bytes / world
+        modes[mode] = {
+            "distribution_ms": td, "distribution_ms_min_max": [td_min, td_max],
+            "source_egress_GBps": sent / td * 1e-6, "receiver_ingress_GBps": recv / td * 1e-6,
+            "frac_of_nvlink_measured_770GBps": sent / td * 1e-6 / NVLINK_MEASURED_GBPS,
+            "frac_of_nvlink_nominal_900GBps": sent / td * 1e-6 / 900.0,
+            "bytes_leaving_source": sent, "bytes_per_receiver": recv,
+            "compute_ms": tc, "aggregate_tflops_compute_only": fl / tc * 1e-9,
+            "total_ms": tb, "total_ms_min_max": [tb_min, tb_max],
+            "aggregate_tflops_incl_distribution": fl / tb * 1e-9,
+            "speedup_vs_n1_incl_distribution": t1 / tb, "efficiency_vs_n1_incl_distribution": t1 / tb / world,
+            "bit_equal_to_single_gpu_run": bool(ok and ok2)}
+        torch.cuda.empty_cache()
+    d = modes["broadcast"]
+    best = min(modes, key=lambda m: modes[m]["total_ms"])
+    floor_ms = qkv_bytes * (world - 1) / world / (NVLINK_MEASURED_GBPS * 1e6)
+    rec.update({
+        "default_mode": "broadcast (one NCCL broadcast of the packed QKV, the north star's wording)",
+        "compute_ms": d["compute_ms"], "bcast_ms": d["distribution_ms"], "bcast_GBps": d["source_egress_GBps"],
+        "aggregate_tflops": d["aggregate_tflops_compute_only"],
+        "aggregate_tflops_incl_distribution": d["aggregate_tflops_incl_distribution"],
+        "efficiency_vs_n1": t1 / d["compute_ms"] / world,
+        "efficiency_vs_n1_incl_distribution": d["efficiency_vs_n1_incl_distribution"],
+        "best_mode": best, "best_total_ms": modes[best]["total_ms"],
+        "best_aggregate_tflops_incl_distribution": modes[best]["aggregate_tflops_incl_distribution"],
+        "best_speedup_vs_n1_incl_distribution": modes[best]["speedup_vs_n1_incl_distribution"],
+        "distribution_floor_ms": floor_ms,
+        "distribution_floor": "inputs start on ONE GPU: (G-1)/G of 12.9 GB must leave rank 0 through its own NVLink ports "
+                              "(measured 770 GB/s per direction); no scheme can finish before that",
+        "best_total_vs_floor": floor_ms / modes[best]["total_ms"],
+        "parity": "every shard bit-equal to rank 0's single-GPU one-call result" if all(
+            m["bit_equal_to_single_gpu_run"] for m in modes.values()) else "MISMATCH",
+        "modes": modes})
+    rec["_launches"] = n_launch
+    del o, qkv, o_full
+    torch.cuda.empty_cache()
+    return rec
+
+
 # ---------------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -256,7 +393,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device. The product path has no CPU fallback; use --impl reference for the CPU arm.")
     torch.cuda.set_device(local_rank)
     if dist_on:
-        os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout; keep stdout = one JSON line
+        # stdout carries exactly one JSON line, and NCCL_DEBUG output goes to stdout by default: send it to a per-rank
+        # file instead and replay it on stderr at the end (so "nranks N" / "Init COMPLETE" stay checkable).
+        nccl_log = None
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            nccl_log = os.path.join(ROOT, "gpurun_out", "nccl_debug_n%d_rank%d.log" % (world, rank))
+            os.environ["NCCL_DEBUG_FILE"] = nccl_log
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -505,30 +648,9 @@ def main():
             torch.cuda.empty_cache()
 
         # -------------------------------------------------------------- config #5: batch-sharded attention over the ranks
-        if dist_on:
-            import torch.distributed as dist
-            from b200k import sharded
-            B_, H_, N_, D_ = FA2_CFG5
-            qkv = torch.randn(3, B_, H_, N_, D_, dtype=torch.half, device=dev) if rank == 0 else None
-            torch.cuda.synchronize()
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            buf = sharded.broadcast_qkv(qkv, (B_, H_, N_, D_), dev)
-            e1.record()
-            torch.cuda.synchronize()
-            t_bcast = max_over_ranks(e0.elapsed_time(e1), True)
-            lo, hi = sharded.shard_bounds(B_, world, rank)
-            o = torch.empty(hi - lo, H_, N_, D_, dtype=torch.half, device=dev)
-            t = cuda_time(lambda: sharded.sharded_attention_fwd(buf, out=o), 5, 2, barrier)
-            launches += 7
-            t = max_over_ranks(t, True)
-            fl = 4.0 * B_ * H_ * N_ * N_ * D_
-            out["attention"]["cfg5_fa2_b32_h64_n8192_d128_sharded"] = {
-                "n_gpus": world, "ms_compute_max_over_ranks": t, "aggregate_tflops": fl / t * 1e-9,
-                "broadcast_ms": t_bcast, "broadcast_GBps": buf.numel() * 2 / t_bcast * 1e-6,
-                "collectives": "one NCCL broadcast of packed QKV (12.9 GB); no reduction; outputs stay sharded", "scaling": "strong"}
-            del buf, o, qkv
+        sharded_rec = bench_sharded_cfg5(world, rank, dev, barrier, dist_on, peaks)
+        launches += sharded_rec.pop("_launches", 0)
+        e2e["sharded_attention"] = sharded_rec
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu_baseline = None
@@ -547,13 +669,23 @@ def main():
                            "l2": "operands 3 x 128 MiB > 126 MB L2 (inputs larger than L2, no flush needed)",
                            "randn_seed": 1},
                 "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "clocks": clocks, "peaks": peaks}
+                "clocks": clocks, "peaks": peaks,
+                "comm": ({"backend": "nccl", "nranks": world, "nccl_version": ".".join(map(str, torch.cuda.nccl.version()))}
+                         if dist_on else None)}
         line.update(out)
         print(json.dumps(line), flush=True)
     if dist_on:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+        if nccl_log and os.path.exists(nccl_log):
+            try:
+                keep = [ln for ln in open(nccl_log, errors="replace") if ("nranks" in ln or "Init COMPLETE" in ln
+                                                                          or "NCCL version" in ln or "NVLS" in ln)]
+                sys.stderr.write("".join(keep[:40]))
+                sys.stderr.flush()
+            except Exception:
+                pass
 
 
 if __name__ == "__main__":

@@ -159,10 +159,12 @@ _ws_cache: dict = {}
 
 
 def _workspace(dev: torch.device) -> torch.Tensor:
-    key = (dev.type, dev.index)
+    """Reduction workspace (partials + ticket), one per (device, stream): two streams running reductions concurrently
+    on one device must not share partials.  The library zeroes the ticket itself on every call."""
+    key = (dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None:
-        ws = torch.zeros(int(_lib.b200k_reduce_workspace_bytes()), dtype=torch.uint8, device=dev)
+        ws = torch.empty(int(_lib.b200k_reduce_workspace_bytes()), dtype=torch.uint8, device=dev)
         _ws_cache[key] = ws
     return ws
 
@@ -204,10 +206,17 @@ def softmax(x, y, mode: int) -> None:
         raise RuntimeError("Tensor size mismatch!")
     _check_cuda_contig(x, y)
     if mode == SOFTMAX_ALL:
-        S, H = 1, x.numel()
-        # row kernels index columns with 32-bit ints: fold a long flat tensor into rows; the total is global anyway
-        if x.dim() >= 2:
-            S, H = x.numel() // x.size(-1), x.size(-1)
+        # The total is global in this mode, so the row shape is free: the reference calls softmax_f32 with a flat
+        # tensor (softmax.py:L63); fold it into rows of the largest power of two <= 4096 dividing numel so that the
+        # normalisation pass runs on the whole grid instead of one CTA.
+        n = x.numel()
+        if x.dim() >= 2 and x.size(-1) <= 16384:
+            S, H = n // x.size(-1), x.size(-1)
+        else:
+            H = 4096
+            while H > 1 and n % H:
+                H //= 2
+            S, H = (n // H, H) if H >= 32 else (1, n)
     else:
         S, H = x.numel() // x.size(-1), x.size(-1)
     with _DeviceGuard(x):

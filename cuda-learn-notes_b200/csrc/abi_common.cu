@@ -2,7 +2,9 @@
 #include "abi_common.cuh"
 
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 
 namespace b200k {
 
@@ -37,6 +39,17 @@ int get_device_info(DeviceInfo* out) {
     return set_error(B200K_EARCH, "libb200k needs a compute-capability 10.x device (B200, sm_100a); device %d is %d.%d",
                      dev, c.cc_major, c.cc_minor);
   *out = c;
+  return B200K_OK;
+}
+
+int ensure_dynamic_smem(const void* func, int device, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> have;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = have.find({func, device});
+  if (it != have.end() && it->second >= bytes) return B200K_OK;
+  B200K_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  have[{func, device}] = bytes;
   return B200K_OK;
 }
 

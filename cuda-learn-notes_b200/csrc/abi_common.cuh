@@ -30,6 +30,11 @@ struct DeviceInfo {
 // Properties of the current device; fails (B200K_EARCH) unless it is compute capability 10.x.
 int get_device_info(DeviceInfo* out);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and per device.  One mutex-protected table for every
+// launcher in the library; a (function, device) pair is recorded only after the attribute call succeeded, and the
+// recorded size only grows, so a transient failure is retried by the next launch instead of poisoning it.
+int ensure_dynamic_smem(const void* func, int device, int bytes);
+
 // 2-D row-major fp16/any-16-bit tensor map: global [rows, cols] (cols contiguous, row pitch `pitch_elems`),
 // box [box_rows, box_cols], 128B swizzle when box_cols*2 == 128, else no swizzle.
 int make_tmap_2d_u16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,

@@ -555,13 +555,7 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
            : poly == 3 ? fa2_fwd_tcgen05_kernel<Cfg, false, P3, DEF_NP>
                        : fa2_fwd_tcgen05_kernel<Cfg, false, P4, DEF_NP>;
   }
-  {  // the dynamic-smem attribute is per function and per device: set it once for each pair
-    static std::mutex mu;
-    static std::set<std::pair<const void*, int>> done;
-    std::lock_guard<std::mutex> lock(mu);
-    if (done.insert({reinterpret_cast<const void*>(kern), di.device}).second)
-      B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), di.device, Cfg::SMEM_BYTES)) return rc;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, tbuf);
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;

@@ -360,6 +360,9 @@ int launch_ffpa_2cta(const void* Q, const void* K, const void* V, void* O, int64
   if ((rc = make_tmap_3d_u16(&tmKh, K, BH, N, D, uint64_t(N) * D, D, 1, 64, 64, 128))) return rc;
   if ((rc = make_tmap_3d_u16(&tmV, V, BH, N, D, uint64_t(N) * D, D, 1, 128, 64, 128))) return rc;
   if ((rc = make_tmap_3d_u16(&tmO, O, BH, N, D, uint64_t(N) * D, D, 1, 32, 64, 128))) return rc;
+  int device = 0;
+  B200K_CHECK_CUDA(cudaGetDevice(&device));
+  struct { int device; } di = {device};
   const bool q_resident = (D <= 512);
   const int q_bytes = q_resident ? int(D / 64) * ffpa2::QBOX : 0;
   int stages = (232448 - 1024 - ffpa2::BAR_BYTES - q_bytes) / ffpa2::STAGE_BYTES;
@@ -381,11 +384,11 @@ int launch_ffpa_2cta(const void* Q, const void* K, const void* V, void* O, int64
   const float scale_log2 = scale * 1.4426950408889634f;
   if (q_resident) {
     auto kern = ffpa2_fwd_tcgen05_kernel<true>;
-    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), di.device, smem)) return rc;
     B200K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQ, tmKh, tmV, tmO, int(N), int(D), stages, scale_log2));
   } else {
     auto kern = ffpa2_fwd_tcgen05_kernel<false>;
-    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), di.device, smem)) return rc;
     B200K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQ, tmKh, tmV, tmO, int(N), int(D), stages, scale_log2));
   }
   return B200K_OK;

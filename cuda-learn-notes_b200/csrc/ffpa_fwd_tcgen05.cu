@@ -455,15 +455,15 @@ extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, v
   const int serial = ((variant & 4) ? 1 : 0) | (((variant >> 6) & 3) << 1);  // bits 6,7: timing probes
   if (q_resident && split) {
     auto kern = ffpa_fwd_tcgen05_kernel<true, 2>;
-    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), di.device, smem)) return rc;
     kern<<<grid, 384, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, serial);
   } else if (q_resident) {
     auto kern = ffpa_fwd_tcgen05_kernel<true, 1>;
-    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), di.device, smem)) return rc;
     kern<<<grid, 256, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, serial);
   } else {
     auto kern = ffpa_fwd_tcgen05_kernel<false, 1>;
-    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), di.device, smem)) return rc;
     kern<<<grid, 256, smem, s>>>(tmQ, tmK, tmV, tmO, int(N), int(D), 256, stages, scale_log2, serial);
   }
   B200K_CHECK_CUDA(cudaGetLastError());

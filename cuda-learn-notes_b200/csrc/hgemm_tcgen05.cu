@@ -311,11 +311,7 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   }
 
   auto kern = hgemm_tcgen05_kernel<Cfg>;
-  static bool attr_set[64] = {};
-  if (!attr_set[di.device]) {
-    B200K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set[di.device] = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), di.device, Cfg::SMEM_BYTES)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * Cfg::CG);
   cfg.blockDim = dim3(256);

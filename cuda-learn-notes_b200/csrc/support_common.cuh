@@ -55,6 +55,17 @@ inline int grid_for(int64_t work_items, int per_block, int sm_count, int waves) 
 }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Workspace of the deterministic two-level reductions (b200k_reduce_workspace_bytes): kReduceMaxBlocks fp32 partials,
+// then 256 bytes holding the ticket counter (and, 128 bytes in, the whole-tensor softmax total).  Every entry point
+// that uses the ticket zeroes it on its own stream first, so a caller may pass any (uninitialised) device buffer and
+// an aborted launch cannot poison the next call.
+constexpr int kReduceMaxBlocks = 2048;
+constexpr size_t kReduceWorkspace = kReduceMaxBlocks * sizeof(float) + 256;
+inline int zero_ticket(void* ws, cudaStream_t s) {
+  B200K_CHECK_CUDA(cudaMemsetAsync(static_cast<char*>(ws) + kReduceMaxBlocks * sizeof(float), 0, 256, s));
+  return B200K_OK;
+}
+
 // e^(x - m) as ex2.approx.ftz(x * log2e - m * log2e): one FFMA and one MUFU.EX2.  (__expf / expf add a denormal-range
 // test and two predicated multiplies per element, which made the f16 softmax instruction-bound; results below 2^-126
 // flush to zero, the relative error is the 2^-22 of the MUFU unit either way.)

@@ -114,8 +114,6 @@ static int launch_add(const void* a, const void* b, void* c, int64_t n, cudaStre
 // ============================================================================================ all-reduce sum
 // Two-level deterministic reduction: every CTA writes one partial, the last CTA to finish (ticket counter) adds the
 // partials in index order.  The reference finishes with atomicAdd(float) in arrival order instead.
-constexpr int kReduceMaxBlocks = 2048;
-constexpr size_t kReduceWorkspace = kReduceMaxBlocks * sizeof(float) + 256;
 
 template <int DT>
 struct Loader;  // sum of one 16-byte pack as float (or int for i8), optional half-precision pack sum
@@ -689,11 +687,6 @@ extern "C" int b200k_elementwise_add(const void* a, const void* b, void* c, int6
 }
 
 extern "C" size_t b200k_reduce_workspace_bytes(void) { return kReduceWorkspace; }
-
-static int zero_ticket(void* ws, cudaStream_t s) {
-  B200K_CHECK_CUDA(cudaMemsetAsync(static_cast<char*>(ws) + kReduceMaxBlocks * sizeof(float), 0, 256, s));
-  return B200K_OK;
-}
 
 extern "C" int b200k_block_all_reduce_sum(const void* x, void* out, int64_t n, int dtype, int acc_f16, void* workspace,
                                           void* stream) {

@@ -263,7 +263,7 @@ static int launch_layer_norm(const void* x, void* y, int64_t rows, int64_t K, fl
 // ============================================================================================ dot product
 // Deterministic two-level reduction (per-CTA partial, the last CTA by ticket adds the partials in index order), as in
 // b200k_block_all_reduce_sum; the reference finishes with atomicAdd(float) in arrival order (dot_product.cu:L52,L76).
-constexpr int kDotMaxBlocks = 2048;  // same workspace layout as the all-reduce: partials, then the ticket
+constexpr int kDotMaxBlocks = kReduceMaxBlocks;  // same workspace layout as the all-reduce: partials, then the ticket
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) dot_kernel(const T* __restrict__ a, const T* __restrict__ b,
@@ -473,19 +473,20 @@ extern "C" int b200k_dot_prod(const void* a, const void* b, void* out, int64_t n
   int rc = get_device_info(&di);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype != B200K_F32 && dtype != B200K_F16)
+    return set_error(B200K_EDTYPE, "b200k_dot_prod: dtype %d not supported (f32, f16)", dtype);
+  if ((rc = zero_ticket(workspace, s))) return rc;
   const bool vec = aligned16(a) && aligned16(b);
   if (dtype == B200K_F32) {
     int grid = grid_for(n / 4, kThreads * 4, di.sm_count, 8);
     if (grid > kDotMaxBlocks) grid = kDotMaxBlocks;
     dot_kernel<float><<<grid, kThreads, 0, s>>>(static_cast<const float*>(a), static_cast<const float*>(b),
                                                 static_cast<float*>(out), n, workspace, vec);
-  } else if (dtype == B200K_F16) {
+  } else {
     int grid = grid_for(n / 8, kThreads * 4, di.sm_count, 8);
     if (grid > kDotMaxBlocks) grid = kDotMaxBlocks;
     dot_kernel<__half><<<grid, kThreads, 0, s>>>(static_cast<const __half*>(a), static_cast<const __half*>(b),
                                                  static_cast<float*>(out), n, workspace, vec);
-  } else {
-    return set_error(B200K_EDTYPE, "b200k_dot_prod: dtype %d not supported (f32, f16)", dtype);
   }
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;

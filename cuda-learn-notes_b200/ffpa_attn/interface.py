@@ -32,6 +32,9 @@ def ffpa_mma_acc_f32_L1(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, O: to
     _ops.ffpa_fwd(Q, K, V, O)
 
 
+_RAW_ENTRY = {MMAAccType.FP32: ffpa_mma_acc_f32_L1, MMAAccType.FP16: ffpa_mma_acc_f16_L1}
+
+
 def faster_prefill_attn_func(
     q: torch.Tensor,
     k: torch.Tensor,
@@ -41,17 +44,15 @@ def faster_prefill_attn_func(
     level: LevelType = LevelType.L1,
     acc: MMAAccType = MMAAccType.FP32,
 ):
-    # Q, K, V, O: [B, H, N, D] layout
-    if not isinstance(o, torch.Tensor) or o is None:
-        o = torch.zeros_like(q)
-    assert level == LevelType.L1, "only support FFPA L1 level now."
-    if acc == MMAAccType.FP32:
-        ffpa_mma_acc_f32_L1(q, k, v, o, num_stages)
-    else:
-        ffpa_mma_acc_f16_L1(q, k, v, o, num_stages)
-    return o
+    """Same signature and defaults as the reference's public entry point (interface.py:L22-39): [B, H, N, D] tensors in,
+    `o` returned (allocated zero-filled when the caller passes none), only level L1 exists."""
+    if level != LevelType.L1:
+        raise AssertionError("only support FFPA L1 level now.")
+    out = o if isinstance(o, torch.Tensor) else torch.zeros_like(q)
+    _RAW_ENTRY[MMAAccType(acc)](q, k, v, out, num_stages)
+    return out
 
 
-ffpa: callable = faster_prefill_attn_func
+ffpa = faster_prefill_attn_func
 ffpa_acc_f32_L1 = partial(faster_prefill_attn_func, level=LevelType.L1, acc=MMAAccType.FP32)
 ffpa_acc_f16_L1 = partial(faster_prefill_attn_func, level=LevelType.L1, acc=MMAAccType.FP16)

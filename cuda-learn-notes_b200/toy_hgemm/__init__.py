@@ -73,10 +73,31 @@ def _make6(name: str, tn: bool):
     return fn
 
 
+def _make_cublas(name: str, tn: bool):
+    """The two `hgemm_cublas_tensor_op_*` names are the reference's COMPARATOR rows (hgemm_cublas.cu:L41-84: cublasGemmEx,
+    CUBLAS_COMPUTE_16F).  They stay a comparator here: the call goes to cuBLAS through torch.matmul, never to the
+    tcgen05 kernel, so the "(cublas)" row of the reference's hgemm.py is what it says it is."""
+    def fn(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> None:
+        if a.dtype != torch.float16 or b.dtype != torch.float16 or c.dtype != torch.float16:
+            raise RuntimeError("values must be torch::kHalf")
+        if not (a.is_cuda and b.is_cuda and c.is_cuda):
+            raise RuntimeError("b200k: tensors must live on a CUDA device (there is no CPU path)")
+        if a.size(1) != b.size(0) or c.size(0) != a.size(0) or c.size(1) != b.size(1):
+            raise RuntimeError("Tensor size mismatch!")
+        if tn and b.is_contiguous():
+            # as_col_major(): a [K,N]-shaped contiguous tensor whose memory is B^T [N,K] row-major (tools/utils.py:L135-140)
+            b = b.reshape(-1).view(b.size(1), b.size(0)).t()
+        torch.matmul(a, b, out=c)
+
+    fn.__name__ = fn.__qualname__ = name
+    fn.__doc__ = name + " (cuBLAS comparator)"
+    return fn
+
+
 for _n in _NN_3ARG:
-    globals()[_n] = _make3(_n, False)
+    globals()[_n] = _make_cublas(_n, False) if "cublas" in _n else _make3(_n, False)
 for _n in _TN_3ARG:
-    globals()[_n] = _make3(_n, True)
+    globals()[_n] = _make_cublas(_n, True) if "cublas" in _n else _make3(_n, True)
 for _n in _NN_STAGED:
     globals()[_n] = _make6(_n, False)
 for _n in _TN_STAGED:

@@ -10,8 +10,10 @@ Products (all optional; every consumer checks for presence):
   oracle/_ref/libref_hgemm.so        C-ABI shim around hgemm_mma_m16n8k16_mma2x4_warp4x4x2_stages_dsmem  (torch-free, ~10 s)
   oracle/_ref/ref_flash_attn_lib.so  torch extension: flash_attn_mma_stages_split_q_shared_qkv{,_acc_f32}  (~2-4 min)
   oracle/_ref/pyffpa_cuda.so         torch extension: the reference's own 3-file FFPA module                (long)
+  oracle/_ref/ref_<op>_lib.so        torch extensions, one per bandwidth-kernel TU of SURVEY 8(a) a6-a12 and 8(f)-3
+                                     (kernels/<op>/<op>.cu with its own PYBIND11_MODULE block; ~1-2 min each, 8 at a time)
 
-usage: python oracle/build_ref.py [hgemm] [flash] [ffpa]      (default: hgemm flash)
+usage: python oracle/build_ref.py [hgemm] [flash] [ffpa] [support]      (default: hgemm flash)
 """
 from __future__ import annotations
 
@@ -108,6 +110,40 @@ def build_ffpa():
     return build_torch_ext("pyffpa_cuda", srcs, inc, defs, jobs=3)
 
 
+# load name -> reference TU (kernels/<dir>/<file>.cu); the names are the ones each <op>.py passes to
+# torch.utils.cpp_extension.load(name=...), prefixed with ref_ so they never collide with the product's shims.
+SUPPORT_TUS = {
+    "elementwise": ("elementwise", "elementwise.cu"), "reduce": ("reduce", "block_all_reduce.cu"),
+    "softmax": ("softmax", "softmax.cu"), "rms_norm": ("rms-norm", "rms_norm.cu"), "rope": ("rope", "rope.cu"),
+    "histogram": ("histogram", "histogram.cu"), "embedding": ("embedding", "embedding.cu"),
+    "relu": ("relu", "relu.cu"), "sigmoid": ("sigmoid", "sigmoid.cu"), "gelu": ("gelu", "gelu.cu"),
+    "swish": ("swish", "swish.cu"), "elu": ("elu", "elu.cu"), "hardswish": ("hardswish", "hardswish.cu"),
+    "hardshrink": ("hardshrink", "hardshrink.cu"), "layer_norm": ("layer-norm", "layer_norm.cu"),
+    "dot_product": ("dot-product", "dot_product.cu"), "mat_transpose": ("mat-transpose", "mat_transpose.cu"),
+    "sgemv": ("sgemv", "sgemv.cu"), "hgemv": ("hgemv", "hgemv.cu"),
+}
+
+
+def build_support(jobs=8):
+    """One torch-extension .so per reference TU, flags as in every kernels/<op>/<op>.py (e.g. rope/rope.py:L13-27)."""
+    procs, rc = [], 0
+    for key, (d, f) in SUPPORT_TUS.items():
+        name = "ref_%s_lib" % key
+        inc, defs, link = torch_flags(name)
+        src = os.path.join(REF, "kernels", d, f)
+        out = os.path.join(OUT, name + ".so")
+        cmd = ["nvcc", *ARCH, *COMMON, *defs, *inc, "-shared", "-x", "cu", src, "-o", out, *link]
+        log = open(os.path.join(OUT, "build_%s.log" % name), "w")
+        procs.append((subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT), src, time.time()))
+        while sum(1 for p, _, _ in procs if p.poll() is None) >= jobs:
+            time.sleep(1)
+    for p, src, t0 in procs:
+        r = p.wait()
+        print("[build_ref] rc=%d %.0fs  %s" % (r, time.time() - t0, src), flush=True)
+        rc |= r
+    return rc
+
+
 def main():
     if not os.path.isdir(REF):
         print("[build_ref] %s not present (GPU box?) - using prebuilt oracle/_ref if any" % REF)
@@ -121,6 +157,8 @@ def main():
         rc |= build_flash()
     if "ffpa" in what:
         rc |= build_ffpa()
+    if "support" in what:
+        rc |= build_support()
     return rc
 
 

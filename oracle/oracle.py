@@ -12,10 +12,13 @@ PINNING STATUS
     fixture (kernels/flash-attn/flash_attn_mma.py:L23-26, L353-369) — see tests/test_oracle.py, tests/golden/.
   * histogram: pinned by the reference fixture list(range(10))*1000 -> 1000 per bin (kernels/histogram/histogram.py:L22-31).
   * HGEMM and the other support kernels: the reference holds NO golden vectors or numeric checks for them
-    (hgemm.py prints two elements) => **parity unpinned** by reference fixtures.  The oracle is
-    instead cross-checked on the GPU box against the reference's own kernels built from /root/reference into
-    oracle/_ref/ (oracle/build_ref.py; tests/test_gpu_vs_reference.py) — the reference is CUDA-only and cannot run
-    in the GPU-less build container.
+    (hgemm.py prints two elements) => unpinned by reference FIXTURES.  They are pinned instead
+    on the GPU box against OUTPUTS OF THE REFERENCE ITSELF: its kernels are built unmodified from /root/reference into
+    oracle/_ref/ by oracle/build_ref.py — `hgemm flash ffpa` (libref_hgemm.so, ref_flash_attn_lib.so, pyffpa_cuda.so;
+    tests/test_gpu_vs_reference.py) and `support` (one ref_<op>_lib.so per bandwidth-kernel TU, 19 of them;
+    tests/test_gpu_vs_reference_support.py runs every exported name of every TU against the product and, for the
+    quirk modes, against this file's restatement).  The reference is CUDA-only and cannot run in the GPU-less build
+    container, so these checks live in the `-m gpu` suite.
 """
 from __future__ import annotations
 

@@ -30,7 +30,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, B, q):
+def _worker(rank, world, port, B, q, mode="legacy"):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, "cuda-learn-notes_b200")]
@@ -53,23 +53,44 @@ def _worker(rank, world, port, B, q):
         oo.copy_(oracle.attention(qq, kk, vv))
 
     lo_hi = sharded.shard_bounds(B, world, rank)
-    o, span = sharded.sharded_attention_fwd(buf, attn_fn=attn)
-    assert span == lo_hi and o.shape[0] == lo_hi[1] - lo_hi[0]
-    gathered = sharded.gather_output(o, B)
     ref = oracle.attention(full[0], full[1], full[2])
-    ok = torch.equal(gathered, ref) and (calls == [o.shape[0]] or o.shape[0] == 0)
+    if mode == "legacy":
+        o, span = sharded.sharded_attention_fwd(buf, attn_fn=attn)
+        assert span == lo_hi and o.shape[0] == lo_hi[1] - lo_hi[0]
+        gathered = sharded.gather_output(o, B)
+        ok = torch.equal(gathered, ref) and (calls == [o.shape[0]] or o.shape[0] == 0)
+    else:
+        # the three input distributions: only rank 0 passes data; every rank must end up with exactly its slice
+        def attn2(qq, kk, vv, oo):
+            calls.append(qq.shape[0])
+            oo.copy_(oracle.attention(qq, kk, vv))
+
+        o, sh = sharded.sharded_attention(full.clone() if rank == 0 else None, (B, H, N, D), torch.device("cpu"),
+                                          mode=mode, attn_fn=attn2, chunk_batches=1)
+        lo, hi = lo_hi
+        ok = sh.span == lo_hi and torch.equal(sh.q, full[0, lo:hi]) and torch.equal(sh.k, full[1, lo:hi]) \
+            and torch.equal(sh.v, full[2, lo:hi])
+        if mode == "pipelined":
+            ok = ok and calls == [1] * (hi - lo)           # one launch per one-batch chunk, in order
+        else:
+            ok = ok and calls == ([hi - lo] if hi > lo else [])
+        if mode != "broadcast" and rank != 0:
+            ok = ok and sh.keep.shape[1] == hi - lo        # a receiver holds 1/G of the bytes, not the whole buffer
+        ok = ok and torch.equal(sharded.gather_output(o, B), ref)
+        ok = ok and sharded.shards_equal_to(o, ref if rank == 0 else None, B)
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B", [4, 3])
-def test_sharded_attention_world2_gloo(B):
+@pytest.mark.parametrize("B,mode", [(4, "legacy"), (3, "legacy"), (4, "broadcast"), (5, "scatter"), (5, "pipelined"),
+                                    (1, "pipelined")])
+def test_sharded_attention_world2_gloo(B, mode):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, B, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, B, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
