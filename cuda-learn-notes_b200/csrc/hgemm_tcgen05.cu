@@ -15,6 +15,10 @@
 //   kernels/hgemm/mma/basic/hgemm_mma_stage.cu:L590-1023 (kernel), L2380-2454 (launcher)  and their NN/TN siblings;
 // the reference's `stages`, `swizzle`, `swizzle_stride` arguments map onto the ring depth (fixed per variant), the
 // hardware 128B swizzle (always on) and the grouped tile rasterisation (GROUP_M) below.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "abi_common.cuh"
 #include "ptx.cuh"
 
@@ -61,11 +65,75 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   *tn = local / gsz;
 }
 
+// Work decomposition.  Tiles [sk_tiles, T) are data-parallel: cluster c owns tiles sk_tiles + c + i*G.  When T is not a
+// multiple of the G resident clusters the remainder r = T mod G would cost a whole extra round on r clusters while G - r
+// idle (8192^3: 1024 tiles on 74 pairs = 13.84 rounds paid as 14; 4096^3: 3.46 paid as 4; 2048^3: 64 tiles on 74
+// pairs).  Those r tiles are done stream-K instead: their r * KB k-blocks are cut into G contiguous, equal ranges, one
+// per cluster, processed BEFORE the cluster's data-parallel tiles.  A range is shorter than one tile (r < G), so it
+// touches at most two tiles: the tail k-blocks of tile j ("writer": fp32 partial sums go to a workspace slot owned by
+// the cluster, then a per-warp flag is set to this launch's epoch) and the head k-blocks of tile j+1 ("finisher": it
+// holds k-block 0, runs second, and its epilogue adds the partials of the clusters that follow it before converting and
+// storing).  Sums are added in a fixed order, so results are deterministic.  All clusters are co-resident (grid <= #SMs,
+// one CTA per SM), which is what lets a finisher wait for its writers.
+struct GemmPlan {
+  int sk_tiles = 0;       // r: tiles [0, r) are stream-K
+  int units_lo = 0;       // every cluster gets units_lo k-blocks of the r * KB, the first units_rem get one more
+  int units_rem = 0;
+  uint32_t epoch = 0;     // value a writer's flag takes in this launch
+  float* partials = nullptr;   // [cluster][cta rank][epilogue warp][32 rows x BN] fp32, layout private to the kernel
+  uint32_t* flags = nullptr;   // [cluster][cta rank][epilogue warp]
+  unsigned long long* trace = nullptr;  // debugging: globaltimer stamps, 128 per cluster (b200k_debug_set_hgemm_trace)
+};
+
+struct WorkItem {
+  int tile, kb0, kb1;
+  int kind;       // 0 = whole tile, 1 = writer (partial sums to the workspace), 2 = finisher (adds the writers' partials)
+  int last_writer;  // finisher: clusters (cluster_id, last_writer] hold the rest of this tile
+};
+
+__device__ __forceinline__ int sk_unit_begin(const GemmPlan& p, int c) { return c * p.units_lo + min(c, p.units_rem); }
+__device__ __forceinline__ int sk_unit_owner(const GemmPlan& p, int x) {
+  const int big = p.units_rem * (p.units_lo + 1);
+  return x < big ? x / (p.units_lo + 1) : p.units_rem + (x - big) / p.units_lo;
+}
+// i-th work item of cluster c (same sequence in the producer, the MMA issuer and the epilogue warps)
+__device__ __forceinline__ WorkItem get_work(const GemmPlan& p, int c, int G, int num_tiles, int num_kb, int i) {
+  WorkItem w;
+  w.kind = -1;  // -1: no more work
+  int n_sk = 0;
+  if (p.sk_tiles > 0) {
+    const int ub = sk_unit_begin(p, c), ue = sk_unit_begin(p, c + 1);
+    if (ub < ue) {
+      const int j0 = ub / num_kb, k0 = ub - j0 * num_kb;
+      const int k1 = min(num_kb, k0 + (ue - ub));
+      const bool two = ue > (j0 + 1) * num_kb;
+      n_sk = two ? 2 : 1;
+      if (i < n_sk) {
+        if (i == 0) { w.tile = j0; w.kb0 = k0; w.kb1 = k1; }
+        else { w.tile = j0 + 1; w.kb0 = 0; w.kb1 = ue - (j0 + 1) * num_kb; }
+        w.kind = (w.kb0 > 0) ? 1 : (w.kb1 < num_kb ? 2 : 0);
+        w.last_writer = (w.kind == 2) ? sk_unit_owner(p, (w.tile + 1) * num_kb - 1) : c;
+        return w;
+      }
+    }
+  }
+  const int t = p.sk_tiles + c + (i - n_sk) * G;
+  w.tile = t; w.kb0 = 0; w.kb1 = num_kb; w.last_writer = c;
+  w.kind = (t < num_tiles) ? 0 : -1;
+  return w;
+}
+
+__device__ __forceinline__ unsigned long long global_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(256, 1)
 hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n,
-                     int group_m, uint64_t policy_a, uint64_t policy_b) {
+                     int group_m, uint64_t policy_a, uint64_t policy_b, const GemmPlan plan) {
   constexpr int CG = Cfg::CG, BN = Cfg::BN, STAGES = Cfg::STAGES;
   constexpr bool B_MN = Cfg::B_MN;
   extern __shared__ uint8_t smem_raw[];
@@ -92,6 +160,8 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int cluster_id = blockIdx.x / CG;
   const int num_clusters = gridDim.x / CG;
 
+  unsigned long long* const trace = plan.trace ? plan.trace + size_t(cluster_id) * 128 : nullptr;
+  if (trace && leader && threadIdx.x == 32) trace[0] = global_timer();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -114,6 +184,7 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if constexpr (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (trace && leader && threadIdx.x == 32) trace[1] = global_timer();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs of a pair)
@@ -122,12 +193,14 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      for (int it = 0;; ++it) {
+        const WorkItem w = get_work(plan, cluster_id, num_clusters, num_tiles, num_kb, it);
+        if (w.kind < 0) break;
         int tm, tn;
-        tile_coords(t, tiles_m, tiles_n, group_m, &tm, &tn);
+        tile_coords(w.tile, tiles_m, tiles_n, group_m, &tm, &tn);
         const int m0 = tm * Cfg::BM + int(cta_rank) * Cfg::BM_CTA;
         const int n0 = tn * BN + int(cta_rank) * Cfg::BN_CTA;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t fb_local = bar_full + 8 * stage;
           const uint32_t sa = smem_tiles + stage * Cfg::STAGE_BYTES;
@@ -181,16 +254,18 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr uint32_t b_kstep = B_MN ? uint32_t(Cfg::UMMA_K) * 128u : 32u;  // bytes per UMMA K step
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      for (int it = 0;; ++it) {
+        const WorkItem w = get_work(plan, cluster_id, num_clusters, num_tiles, num_kb, it);
+        if (w.kind < 0) break;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
+          if (trace && it == 0 && kb == w.kb0 && lane == 0) trace[2] = global_timer();
           const uint32_t sa = smem_tiles + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           if (elect_one()) {
@@ -198,11 +273,11 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; ++k) {
               const uint64_t adesc = smem_desc(a_hi, sa + k * 32);
               const uint64_t bdesc = smem_desc(b_hi, sb + k * b_kstep);
-              umma_ss<CG, (Cfg::DT == 2)>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss<CG, (Cfg::DT == 2)>(d_tmem, adesc, bdesc, idesc, (kb > w.kb0 || k != 0) ? 1u : 0u);
             }
             if constexpr (CG == 2) umma_commit_2sm(bar_empty + 8 * stage, 0b11);
             else umma_commit(bar_empty + 8 * stage);
-            if (kb == num_kb - 1) {  // accumulator complete: publish it to the epilogue warps
+            if (kb == w.kb1 - 1) {  // accumulator complete: publish it to the epilogue warps
               if constexpr (CG == 2) umma_commit_2sm(bar_tfull + 8 * acc, 0b11);
               else umma_commit(bar_tfull + 8 * acc);
             }
@@ -210,6 +285,7 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (trace && it < 56 && lane == 0) trace[8 + it] = global_timer();
       }
     }
   } else if (warp >= 4) {
@@ -217,10 +293,11 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t q = warp & 3;  // TMEM lane quadrant this warp may read
     const uint32_t epi = smem_epi + q * Cfg::EPI_WARP_BYTES;
     uint32_t nbuf = 0;
-    int it = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+    for (int it = 0;; ++it) {
+      const WorkItem w = get_work(plan, cluster_id, num_clusters, num_tiles, num_kb, it);
+      if (w.kind < 0) break;
       int tm, tn;
-      tile_coords(t, tiles_m, tiles_n, group_m, &tm, &tn);
+      tile_coords(w.tile, tiles_m, tiles_n, group_m, &tm, &tn);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = tm * Cfg::BM + int(cta_rank) * Cfg::BM_CTA + int(q) * 32;
@@ -228,6 +305,21 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after();
       // one chunk = 32 rows x 128 bytes of C per warp: 64 columns of 16-bit output or 32 columns of fp32
       constexpr int CC = Cfg::ROW_ELEMS;
+      // stream-K: this warp's 32 x BN slice of a cluster's partial tile, stored as [chunk][16-byte unit][lane] so that
+      // every warp-wide access is one contiguous 512-byte segment
+      constexpr int WARP_PARTIAL = 32 * BN;  // floats
+      const size_t my_slot = (size_t(cluster_id) * CG + cta_rank) * 4 + q;
+      if (w.kind == 2) {
+        // finisher: wait until every writer of this tile has published this warp's slice (flag == epoch)
+        for (int cc = cluster_id + 1; cc <= w.last_writer; ++cc) {
+          const volatile uint32_t* f = plan.flags + (size_t(cc) * CG + cta_rank) * 4 + q;
+          const long long t0 = clock64();
+          while (*f != plan.epoch) {
+            if (clock64() - t0 > B200K_SPIN_LIMIT_CYCLES) __trap();
+          }
+        }
+        __threadfence();
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / CC; ++c) {
         uint32_t r[CC];
@@ -242,6 +334,27 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (lane == 0) {
             if constexpr (CG == 2) mbar_arrive_cluster(mapa(bar_tempty + 8 * acc, 0));
             else mbar_arrive(bar_tempty + 8 * acc);
+          }
+        }
+        if (w.kind == 1) {
+          // writer: raw fp32 partial sums to this cluster's workspace slot
+          uint4* dst = reinterpret_cast<uint4*>(plan.partials + my_slot * WARP_PARTIAL) + size_t(c) * (CC / 4) * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < CC / 4; ++j) dst[j * 32] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          continue;
+        }
+        if (w.kind == 2) {
+          for (int cc = cluster_id + 1; cc <= w.last_writer; ++cc) {   // fixed order: deterministic sums
+            const uint4* src = reinterpret_cast<const uint4*>(plan.partials + ((size_t(cc) * CG + cta_rank) * 4 + q) * WARP_PARTIAL) +
+                               size_t(c) * (CC / 4) * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < CC / 4; ++j) {
+              const uint4 v = __ldcg(src + j * 32);
+              r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + __uint_as_float(v.x));
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + __uint_as_float(v.y));
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + __uint_as_float(v.z));
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + __uint_as_float(v.w));
+            }
           }
         }
         const uint32_t buf = epi + (nbuf & 1) * 4096;
@@ -273,14 +386,55 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tma_store_commit();
         }
       }
+      if (w.kind == 1) {
+        // publish: all lanes' partial stores, then the flag (the finisher's matching warp polls it)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(plan.flags + my_slot) = plan.epoch;
+      }
+      if (trace && leader && warp == 4 && it < 56 && lane == 0) trace[64 + it] = global_timer();
     }
     if (lane == 0) tma_store_wait_all<0>();
     __syncwarp();
+    if (trace && leader && warp == 4 && lane == 0) trace[3] = global_timer();
   }
 
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 2) tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+}
+
+// Stream-K workspace: one per (device, stream), allocated on first use and kept (like a BLAS handle's workspace), so
+// that launches on different streams never share partial sums.  Flags are compared against a per-workspace launch
+// counter ("epoch"), so nothing has to be cleared between launches.  First use on a stream calls cudaMalloc: warm up
+// before capturing a CUDA graph.
+struct SkWorkspace {
+  float* partials = nullptr;
+  uint32_t* flags = nullptr;
+  size_t partial_bytes = 0;
+  uint32_t epoch = 0;
+};
+static unsigned long long* g_hgemm_trace = nullptr;  // b200k_debug_set_hgemm_trace()
+
+static int get_sk_workspace(int device, cudaStream_t stream, size_t partial_bytes, SkWorkspace** out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SkWorkspace> table;
+  constexpr size_t kFlagBytes = 4096;  // 128 clusters x 2 CTAs x 4 warps x 4 B
+  std::lock_guard<std::mutex> lock(mu);
+  SkWorkspace& w = table[{device, stream}];
+  if (w.partial_bytes < partial_bytes) {
+    if (w.partials) B200K_CHECK_CUDA(cudaFree(w.partials));
+    w = SkWorkspace();
+    void* p = nullptr;
+    B200K_CHECK_CUDA(cudaMalloc(&p, partial_bytes + kFlagBytes));
+    B200K_CHECK_CUDA(cudaMemset(static_cast<char*>(p) + partial_bytes, 0, kFlagBytes));
+    w.partials = static_cast<float*>(p);
+    w.flags = reinterpret_cast<uint32_t*>(static_cast<char*>(p) + partial_bytes);
+    w.partial_bytes = partial_bytes;
+  }
+  ++w.epoch;
+  *out = &w;
+  return B200K_OK;
 }
 
 template <class Cfg>
@@ -298,7 +452,24 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   const int tiles_n = int((N + Cfg::BN - 1) / Cfg::BN);
   const int64_t num_tiles = int64_t(tiles_m) * tiles_n;
   const int max_clusters = di.sm_count / Cfg::CG;
-  const int clusters = int(num_tiles < max_clusters ? num_tiles : max_clusters);
+  int clusters = int(num_tiles < max_clusters ? num_tiles : max_clusters);
+  // Stream-K for the remainder round (see GemmPlan); tune bit 20 switches it off (A/B measurements).
+  GemmPlan plan;
+  plan.trace = g_hgemm_trace;
+  const int num_kb = int((K + Cfg::BK - 1) / Cfg::BK);
+  const int64_t rem_tiles = num_tiles % max_clusters;
+  if (rem_tiles != 0 && num_kb >= 8 && max_clusters <= 128 && !((tune >> 20) & 1)) {
+    const int64_t units = rem_tiles * num_kb;
+    SkWorkspace* ws = nullptr;
+    if ((rc = get_sk_workspace(di.device, stream, size_t(max_clusters) * Cfg::CG * 128 * Cfg::BN * sizeof(float), &ws))) return rc;
+    clusters = max_clusters;
+    plan.sk_tiles = int(rem_tiles);
+    plan.units_lo = int(units / clusters);
+    plan.units_rem = int(units % clusters);
+    plan.epoch = ws->epoch;
+    plan.partials = ws->partials;
+    plan.flags = ws->flags;
+  }
   // tune (experiments): bits [8,16) override GROUP_M, bits [16,20) select the L2 eviction hints of the TMA loads.
   int group_m = 8;
   if ((tune >> 8) & 0xff) group_m = (tune >> 8) & 0xff;
@@ -324,7 +495,7 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, int(M), int(N), int(K), tiles_m, tiles_n, group_m, policy_a, policy_b));
+  B200K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, int(M), int(N), int(K), tiles_m, tiles_n, group_m, policy_a, policy_b, plan));
   return B200K_OK;
 }
 
@@ -371,6 +542,14 @@ static int gemm_dispatch(const char* who, const void* A, const void* B, void* C,
   }
 }
 }  // namespace b200k
+
+// Debug hook (not part of the drop-in surface): device buffer of 128 uint64 per cluster (74 x 128 for the pair kernels)
+// that every following GEMM launch fills with %globaltimer stamps: [0] kernel entry, [1] set-up done, [2] first operand
+// stage landed, [3] last store done, [8+i] MMAs of work item i issued, [64+i] epilogue of item i done.  nullptr = off.
+extern "C" int b200k_debug_set_hgemm_trace(void* dev_u64_buffer) {
+  b200k::g_hgemm_trace = static_cast<unsigned long long*>(dev_u64_buffer);
+  return B200K_OK;
+}
 
 extern "C" int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk,
                                int variant, void* stream) {

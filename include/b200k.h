@@ -177,6 +177,8 @@ int b200k_gemv(const void* a, const void* x, void* y, int64_t M, int64_t K, int 
 /* Debug hook, not part of the drop-in surface: device buffer of 3*32*8 uint64 that the next traced FA-2 launch
  * (variant | 0x100, D = 64 or 128) fills with clock64() stamps of CTA (0,0); see tools/gpu_trace_fa2.py. */
 int b200k_debug_set_trace(void* dev_u64_buffer);
+/* Debug hook of the GEMM kernel: 128 uint64 %globaltimer stamps per cluster (see hgemm_tcgen05.cu); NULL switches it off. */
+int b200k_debug_set_hgemm_trace(void* dev_u64_buffer);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,151 @@
+"""Round-2 HGEMM experiments on the B200 box (one process, round-robin timing; writes gpurun_out/r2/hgemm_r2.jsonl).
+  check   correctness of the stream-K remainder round (vs fp64 samples, determinism, stream-K on/off closeness)
+  time    round-robin TFLOP/s: cuBLAS (torch.matmul), ours default, stream-K off, GROUP_M / L2-policy variants
+  trace   %globaltimer stamps of every cluster at 8192^3 (b200k_debug_set_hgemm_trace)
+  ncu     launches each variant once at 8192^3 (run under `ncu --metrics dram__bytes...`)
+"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "cuda-learn-notes_b200"))
+import torch
+from b200k import ops, _loader as L
+
+OUT = os.path.join(ROOT, "gpurun_out", "r2")
+os.makedirs(OUT, exist_ok=True)
+SK_OFF = 1 << 20
+V2 = 2  # B200K_HGEMM_2CTA_256x256
+
+
+def emit(rec, f):
+    print(json.dumps(rec), flush=True)
+    f.write(json.dumps(rec) + "\n")
+    f.flush()
+
+
+def timeit(fn, iters):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def check(f):
+    torch.manual_seed(0)
+    for (M, N, K) in [(2048, 2048, 2048), (4096, 4096, 4096), (1000, 1256, 2048), (256, 512, 4096), (8192, 8192, 512),
+                      (3072, 5120, 1024), (8192, 8192, 8192), (128, 256, 64), (2304, 2048, 8192)]:
+        a = torch.randn(M, K, dtype=torch.half, device="cuda")
+        b = torch.randn(K, N, dtype=torch.half, device="cuda")
+        c1 = torch.full((M, N), float("nan"), dtype=torch.half, device="cuda")
+        c2 = torch.full((M, N), float("nan"), dtype=torch.half, device="cuda")
+        c3 = torch.full((M, N), float("nan"), dtype=torch.half, device="cuda")
+        ops.hgemm(a, b, c1)
+        ops.hgemm(a, b, c2)
+        ops.hgemm(a, b, c3, variant=V2 | SK_OFF)
+        torch.cuda.synchronize()
+        rows = torch.randint(0, M, (64,), device="cuda")
+        exact = (a[rows].double() @ b.double())
+        err = (c1[rows].double() - exact).abs().max().item()
+        rec = {"what": "check", "mnk": [M, N, K], "finite": bool(torch.isfinite(c1).all()), "deterministic": bool(torch.equal(c1, c2)),
+               "max_err_vs_fp64_rows": err, "bound": float(exact.abs().max().item() * 2.0 ** -10),
+               "max_diff_sk_on_off": float((c1.float() - c3.float()).abs().max().item()),
+               "frac_bit_equal_on_off": float((c1 == c3).float().mean().item())}
+        rec["ok"] = rec["finite"] and rec["deterministic"] and err <= rec["bound"] and rec["max_diff_sk_on_off"] <= rec["bound"]
+        emit(rec, f)
+        # TN twin
+        bt = b.t().contiguous()
+        c4 = torch.full((M, N), float("nan"), dtype=torch.half, device="cuda")
+        ops.hgemm(a, bt.t(), c4, tn=True)
+        emit({"what": "check_tn", "mnk": [M, N, K], "equal_to_nn": bool(torch.equal(c4, c1)),
+              "max_diff": float((c4.float() - c1.float()).abs().max().item())}, f)
+        del a, b, c1, c2, c3, c4, bt
+
+
+def time_all(f, sizes, rounds):
+    for n in sizes:
+        torch.manual_seed(1)
+        a = torch.randn(n, n, dtype=torch.half, device="cuda")
+        b = torch.randn(n, n, dtype=torch.half, device="cuda")
+        c = torch.empty(n, n, dtype=torch.half, device="cuda")
+        cfgs = {"cublas": None, "default": 0, "sk_off": V2 | SK_OFF}
+        for gm in (4, 16, 32):
+            cfgs["gm%d" % gm] = V2 | (gm << 8)
+        for pol in (1, 2, 3):
+            cfgs["gm8_pol%d" % pol] = V2 | (pol << 16)
+        cfgs["gm16_pol1"] = V2 | (16 << 8) | (1 << 16)
+        res = {k: [] for k in cfgs}
+        fl = 2.0 * n ** 3
+        iters = 20 if n <= 8192 else 4
+        fns = {k: ((lambda: torch.matmul(a, b, out=c)) if v is None else (lambda v=v: ops.hgemm(a, b, c, variant=v))) for k, v in cfgs.items()}
+        for k in cfgs:
+            timeit(fns[k], 3)
+        for r in range(rounds):
+            for k in cfgs:
+                res[k].append(fl / timeit(fns[k], iters) * 1e-9)
+        for k, v in res.items():
+            v2 = sorted(v)
+            emit({"what": "time", "n": n, "cfg": k, "median": v2[len(v2) // 2], "min": v2[0], "max": v2[-1], "all": [round(x) for x in v]}, f)
+        del a, b, c
+
+
+def trace(f, n=8192):
+    a = torch.randn(n, n, dtype=torch.half, device="cuda")
+    b = torch.randn(n, n, dtype=torch.half, device="cuda")
+    c = torch.empty(n, n, dtype=torch.half, device="cuda")
+    buf = torch.zeros(74 * 128, dtype=torch.int64, device="cuda")
+    for name, v in (("default", 0), ("sk_off", V2 | SK_OFF)):
+        for _ in range(3):
+            ops.hgemm(a, b, c, variant=v)
+        torch.cuda.synchronize()
+        L.lib.b200k_debug_set_hgemm_trace(buf.data_ptr())
+        buf.zero_()
+        ops.hgemm(a, b, c, variant=v)
+        torch.cuda.synchronize()
+        L.lib.b200k_debug_set_hgemm_trace(None)
+        t = buf.cpu().view(74, 128)
+        t0 = int(t[:, 0][t[:, 0] > 0].min())
+        rel = lambda x: [int(v - t0) if v > 0 else None for v in x.tolist()]
+        entry, setup, first, end = rel(t[:, 0]), rel(t[:, 1]), rel(t[:, 2]), rel(t[:, 3])
+        mma = [[int(v - t0) for v in row.tolist() if v > 0] for row in t[:, 8:64]]
+        epi = [[int(v - t0) for v in row.tolist() if v > 0] for row in t[:, 64:120]]
+        emit({"what": "trace", "n": n, "cfg": name, "unit": "ns since first cluster's kernel entry",
+              "entry_min_max": [min(entry), max(entry)], "setup_done_min_max": [min(setup), max(setup)],
+              "first_stage_landed_min_max": [min(x for x in first if x is not None), max(x for x in first if x is not None)],
+              "end_min_max": [min(end), max(end)], "end_sorted": sorted(end),
+              "items_per_cluster": sorted(set(len(m) for m in mma)),
+              "cluster0_mma_issue_done": mma[0], "cluster73_mma_issue_done": mma[73],
+              "cluster0_epilogue_done": epi[0], "cluster73_epilogue_done": epi[73],
+              "last_mma_issue_min_max": [min(m[-1] for m in mma), max(m[-1] for m in mma)]}, f)
+
+
+def ncu_launches(n=8192):
+    a = torch.randn(n, n, dtype=torch.half, device="cuda")
+    b = torch.randn(n, n, dtype=torch.half, device="cuda")
+    c = torch.empty(n, n, dtype=torch.half, device="cuda")
+    order = [("default", 0), ("sk_off", V2 | SK_OFF)]
+    for gm in (4, 8, 16, 32):
+        for pol in (0, 1, 3):
+            order.append(("gm%d_pol%d" % (gm, pol), V2 | (gm << 8) | (pol << 16)))
+    for name, v in order:
+        ops.hgemm(a, b, c, variant=v)
+        torch.cuda.synchronize()
+        print("NCU_ORDER", name, flush=True)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    print("NCU_ORDER cublas", flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1]
+    with open(os.path.join(OUT, "hgemm_r2.jsonl"), "a") as f:
+        if what == "check":
+            check(f)
+        elif what == "time":
+            time_all(f, [int(x) for x in sys.argv[2].split(",")], int(sys.argv[3]))
+        elif what == "trace":
+            trace(f)
+        elif what == "ncu":
+            ncu_launches()
