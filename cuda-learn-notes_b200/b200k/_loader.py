@@ -27,7 +27,7 @@ OK, EDTYPE, ESHAPE, EALIGN, EHEADDIM, ECUDA, EARCH, EARG = 0, -1, -2, -3, -4, -5
 # dtype enums (include/b200k.h)
 F32, F16, BF16, I8, FP8_E4M3, FP8_E5M2, I32 = 0, 1, 2, 3, 4, 5, 6
 
-HGEMM_AUTO, HGEMM_1CTA_128x256, HGEMM_2CTA_256x256, HGEMM_2CTA_256x128 = 0, 1, 2, 3
+HGEMM_AUTO, HGEMM_1CTA_128x256, HGEMM_2CTA_256x256, HGEMM_2CTA_256x128, HGEMM_2CTA_512x256 = 0, 1, 2, 3, 4
 
 # activation ops (include/b200k.h)
 ACT_RELU, ACT_SIGMOID, ACT_GELU, ACT_SWISH, ACT_ELU, ACT_HARDSWISH, ACT_HARDSHRINK = range(7)
@@ -58,8 +58,10 @@ _SIGS = {
     "b200k_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "b200k_hgemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "b200k_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
+    "b200k_gemm_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "b200k_fa2_fwd_f16": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_float, c_int, c_int, c_void_p]),
     "b200k_ffpa_fwd_f16": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_float, c_int, c_void_p]),
+    "b200k_fa2_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_float, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "b200k_elementwise_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b200k_reduce_workspace_bytes": (c_size_t, []),
     "b200k_block_all_reduce_sum": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),

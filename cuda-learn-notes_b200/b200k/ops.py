@@ -98,9 +98,24 @@ def hgemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, tn: bool = False, v
                                      _stream(a)))
 
 
-def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, tn: bool = False, variant: int = L.HGEMM_AUTO) -> None:
+def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, tn: bool = False, variant: int = L.HGEMM_AUTO,
+         a_km: bool = False) -> None:
     """c = a @ B for fp16, bf16 (fp32 accumulation) or fp32 operands (TF32 tensor-core product, fp32 accumulation and
-    output); same layouts as :func:`hgemm`."""
+    output); same layouts as :func:`hgemm`.  ``a_km``: ``a`` has logical shape [M,K] but its storage is A^T [K,M] row-major
+    (pass ``At.t()`` of a contiguous ``At``) - the BLAS "NT"/"TT" cases, f16 / bf16."""
+    if a_km:
+        if a.dtype not in (torch.float16, torch.bfloat16):
+            raise RuntimeError("values must be torch::kHalf or torch::kBFloat16")
+        _check_dtype(b, a.dtype)
+        _check_dtype(c, a.dtype)
+        M, K, N = a.size(0), a.size(1), b.size(1)
+        if b.size(0) != K or c.size(0) != M or c.size(1) != N:
+            raise RuntimeError("Tensor size mismatch!")
+        _check_cuda_contig(a.t(), (b if b.is_contiguous() else b.t()) if tn else b, c)
+        with _DeviceGuard(a):
+            L.check(_lib.b200k_gemm_ex(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, 1, 1 if tn else 0,
+                                       _DTYPE_ENUM[a.dtype], variant, _stream(a)))
+        return
     if a.dtype not in (torch.float16, torch.bfloat16, torch.float32):
         raise RuntimeError("values must be torch::kHalf, torch::kBFloat16 or torch::kFloat32")
     _check_dtype(b, a.dtype)
@@ -122,9 +137,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, tn: bool = False, va
 FA2_HEADDIMS = (32, 64, 96, 128)
 
 
-def _check_qkvo(q, k, v, o, v_is_dn=False):
+def _check_qkvo(q, k, v, o, v_is_dn=False, dtype=torch.float16):
     for t in (q, k, v, o):
-        _check_dtype(t, torch.float16)
+        _check_dtype(t, dtype)
     if q.dim() != 4:
         raise RuntimeError("Tensor size mismatch!")
     B, H, N, D = q.shape
@@ -135,13 +150,29 @@ def _check_qkvo(q, k, v, o, v_is_dn=False):
     return B, H, N, D
 
 
-def fa2_fwd(q, k, v, o, scale: Optional[float] = None, v_is_dn: bool = False, variant: int = 0) -> None:
-    B, H, N, D = _check_qkvo(q, k, v, o, v_is_dn)
+def fa2_fwd(q, k, v, o, scale: Optional[float] = None, v_is_dn: bool = False, variant: int = 0, causal: bool = False,
+            seqlens_k: Optional[torch.Tensor] = None) -> None:
+    """FA-2 forward, [B,H,N,D] fp16 (the reference's layout and dtype) or bf16.  ``causal`` and ``seqlens_k`` (int32 [B] on
+    the device: valid keys per batch) are the caller-facing options of SURVEY 8(f)-4; the reference has neither."""
+    dt = q.dtype if q.dtype == torch.bfloat16 else torch.float16
+    B, H, N, D = _check_qkvo(q, k, v, o, v_is_dn, dt)
     if D not in FA2_HEADDIMS:
         raise RuntimeError("headdim not support!")
+    sl = 0
+    if seqlens_k is not None:
+        _check_dtype(seqlens_k, torch.int32)
+        _check_cuda_contig(seqlens_k)
+        if seqlens_k.numel() != B:
+            raise RuntimeError("Tensor size mismatch!")
+        sl = seqlens_k.data_ptr()
     with _DeviceGuard(q):
-        L.check(_lib.b200k_fa2_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, D,
-                                       float(scale) if scale else 0.0, 1 if v_is_dn else 0, variant, _stream(q)))
+        if dt == torch.float16 and not causal and seqlens_k is None:
+            L.check(_lib.b200k_fa2_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, D,
+                                           float(scale) if scale else 0.0, 1 if v_is_dn else 0, variant, _stream(q)))
+        else:
+            L.check(_lib.b200k_fa2_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, D,
+                                       float(scale) if scale else 0.0, 1 if v_is_dn else 0, _DTYPE_ENUM[dt],
+                                       1 if causal else 0, sl, variant, _stream(q)))
 
 
 def ffpa_fwd(q, k, v, o, scale: Optional[float] = None, variant: int = 0) -> None:

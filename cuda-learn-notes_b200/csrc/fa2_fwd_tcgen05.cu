@@ -35,9 +35,10 @@
 
 namespace b200k {
 
-template <int D_, int BC_, int STAGES_, bool V_DN_ = false, bool ALIAS_P_ = false, bool SHARE_S_ = false>
+template <int D_, int BC_, int STAGES_, bool V_DN_ = false, bool ALIAS_P_ = false, bool SHARE_S_ = false, int DT_ = 0>
 struct Fa2Cfg {
   static constexpr int D = D_;
+  static constexpr int DT = DT_;  // 0: fp16 Q/K/V/O and P; 1: bf16 (same kernel: kind::f16 with bf16 operand formats)
   static constexpr int BC = BC_;                       // keys per KV tile
   static constexpr int STAGES = STAGES_;
   // ALIAS_P: P overwrites the first BC/2 columns of S (needed when S0 S1 O0 O1 already fill the 512 columns, i.e.
@@ -83,11 +84,21 @@ constexpr float kRescaleThreshold = 8.0f;
 constexpr int kTraceIters = 32, kTraceEvents = 8;
 static unsigned long long* g_fa2_trace = nullptr;  // set through b200k_debug_set_trace()
 
+// Masks (the reference has none).  causal: query row r attends keys <= r; KV tiles entirely above the
+// diagonal of BOTH Q tiles of the CTA are never loaded or multiplied (half the work at large N), tiles that touch the
+// diagonal get an element mask.  seqlens (int32 [B], optional): keys >= seqlens[b] are masked for batch b ("varlen" in
+// the padded [B,H,N,D] layout, i.e. a key-padding mask); every query row of the batch is still computed.
+struct Fa2Mask {
+  const int* seqlens = nullptr;
+  int H = 1;
+  int causal = 0;
+};
+
 template <class Cfg, bool TRACE, int POLY, int NP>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int N,
-                       float scale_log2, unsigned long long* trace) {
+                       float scale_log2, unsigned long long* trace, const Fa2Mask mask) {
   auto tr = [&](int role, int j, int ev) {
     if constexpr (TRACE) {
       if (blockIdx.x == 0 && blockIdx.y == 0 && j < kTraceIters)
@@ -121,8 +132,11 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
-  const int q0 = blockIdx.x * 256;
-  const int T = (N + BC - 1) / BC;  // KV tiles
+  // causal: CTAs near the end of the sequence have the most KV tiles; start them first
+  const int q0 = (mask.causal ? int(gridDim.x - 1 - blockIdx.x) : int(blockIdx.x)) * 256;
+  const int n_keys = mask.seqlens ? min(N, max(1, mask.seqlens[bh / mask.H])) : N;  // valid keys of this batch
+  const int Tk = (n_keys + BC - 1) / BC;
+  const int T = mask.causal ? min(Tk, (q0 + 256 + BC - 1) / BC) : Tk;  // KV tiles this CTA walks
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -213,9 +227,9 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     // ---------------------------------------------------------------------------------- MMA issuer
     // One lane is elected once and runs the whole issue loop (see the producer above).
     if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_f16(128, BC, true, false, false);  // Q, K both K-major (D contiguous)
+      constexpr uint32_t idesc_s = make_idesc(128, BC, Cfg::DT, false, false);  // Q, K both K-major (D contiguous)
       // P from TMEM; V is MN-major ([keys, D], D contiguous) or, for V^T input, K-major ([D, keys], keys contiguous)
-      constexpr uint32_t idesc_o = make_idesc_f16(128, D, true, false, !Cfg::V_DN);
+      constexpr uint32_t idesc_o = make_idesc(128, D, Cfg::DT, false, !Cfg::V_DN);
       constexpr uint64_t qk_hi = make_smem_desc_hi(16, 8 * ROWB, Cfg::SWZ_MODE);
       constexpr uint64_t v_hi = Cfg::V_DN ? make_smem_desc_hi(16, 1024, kSwizzle128B)
                                           : make_smem_desc_hi(Cfg::KV_CHUNK_BYTES, 8 * ROWB, Cfg::SWZ_MODE);
@@ -377,14 +391,22 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (lane == 0) mbar_arrive(bar_s_free + 8 * i);
       }
       float* s = reinterpret_cast<float*>(sr);
-      if (j == T - 1 && (N % BC) != 0) {
+      if (j == Tk - 1 && (n_keys % BC) != 0) {
         // ragged last tile only.  The empty asm keeps this a real (warp-uniform) branch: if-converted, the 2 x BC
         // compare/select instructions would run on every tile.
         asm volatile("" ::: "memory");
-        const int valid = N - j * BC;
+        const int valid = n_keys - j * BC;
 #pragma unroll
         for (int c = 0; c < BC; ++c)
           if (c >= valid) s[c] = -INFINITY;
+      }
+      if (mask.causal && (j + 1) * BC - 1 > q0 + i * 128 + int(q) * 32) {
+        // this KV tile reaches past the diagonal for some row of the warp (warp-uniform test on the warp's first row)
+        asm volatile("" ::: "memory");
+        const int last = q0 + i * 128 + int(q) * 32 + int(lane) - j * BC;  // last visible key of this row, tile-relative
+#pragma unroll
+        for (int c = 0; c < BC; ++c)
+          if (c > last) s[c] = -INFINITY;
       }
       const float mx = row_max<BC>(s) * scale_log2;
       // Has PV_i(j-1) been observed complete (O_i stable, P_i columns free)?  With ALIAS_P it always has: S_i(j) was
@@ -446,8 +468,8 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int e = 0; e < 8; e += 2) {
           acc0 = fadd2(acc0, x[e]);
           acc1 = fadd2(acc1, x[e + 1]);
-          sr[(c0 >> 1) + e] = pack_half2(x[e].x, x[e].y);
-          sr[(c0 >> 1) + e + 1] = pack_half2(x[e + 1].x, x[e + 1].y);
+          sr[(c0 >> 1) + e] = Cfg::DT == 1 ? pack_bf162(x[e].x, x[e].y) : pack_half2(x[e].x, x[e].y);
+          sr[(c0 >> 1) + e + 1] = Cfg::DT == 1 ? pack_bf162(x[e + 1].x, x[e + 1].y) : pack_half2(x[e + 1].x, x[e + 1].y);
         }
         if ((c0 + 16) % PIECE == 0) {
           // piece complete: hand it to the MMA thread now, PV of this piece runs under the next piece's exponentials
@@ -485,9 +507,14 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const float* f = reinterpret_cast<const float*>(orr + 8 * g);
-        st_shared_v4(row_addr + (((sub0 + g) ^ xr) << 4), pack_half2(f[0] * inv_l, f[1] * inv_l),
-                     pack_half2(f[2] * inv_l, f[3] * inv_l), pack_half2(f[4] * inv_l, f[5] * inv_l),
-                     pack_half2(f[6] * inv_l, f[7] * inv_l));
+        if constexpr (Cfg::DT == 1)
+          st_shared_v4(row_addr + (((sub0 + g) ^ xr) << 4), pack_bf162(f[0] * inv_l, f[1] * inv_l),
+                       pack_bf162(f[2] * inv_l, f[3] * inv_l), pack_bf162(f[4] * inv_l, f[5] * inv_l),
+                       pack_bf162(f[6] * inv_l, f[7] * inv_l));
+        else
+          st_shared_v4(row_addr + (((sub0 + g) ^ xr) << 4), pack_half2(f[0] * inv_l, f[1] * inv_l),
+                       pack_half2(f[2] * inv_l, f[3] * inv_l), pack_half2(f[4] * inv_l, f[5] * inv_l),
+                       pack_half2(f[6] * inv_l, f[7] * inv_l));
       }
     }
     fence_proxy_async_smem();
@@ -509,7 +536,8 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
 template <class Cfg>
 static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N, float scale,
-                      cudaStream_t stream, const DeviceInfo& di, int np = 0, bool trace = false, int poly = 0) {
+                      cudaStream_t stream, const DeviceInfo& di, int np = 0, bool trace = false, int poly = 0,
+                      const Fa2Mask mask = Fa2Mask()) {
   constexpr int D = Cfg::D;
   const uint64_t BH = uint64_t(B) * uint64_t(H);
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -529,12 +557,12 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
   dim3 grid(unsigned((N + 255) / 256), unsigned(BH));
   const float scale_log2 = scale * 1.4426950408889634f;
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, int, float,
-                        unsigned long long*);
+                        unsigned long long*, const Fa2Mask);
   Kern kern;
   unsigned long long* tbuf = nullptr;
   // Experiment / debug instantiations (piece counts, cycle trace, higher polynomial fractions) only exist for the two
   // benchmark shapes; every configuration has the production pair (POLY 0 and 1, two pieces).
-  constexpr bool kLab = (Cfg::D == 64 || Cfg::D == 128) && !Cfg::V_DN && Cfg::BC == 128;
+  constexpr bool kLab = (Cfg::D == 64 || Cfg::D == 128) && !Cfg::V_DN && Cfg::BC == 128 && Cfg::DT == 0;
   // Pieces per KV tile in which P is handed to the MMA thread.  With the shared S buffer PV is off the critical chain
   // and one hand-over per tile is best (D = 128: 1 -> 1267, 2 -> 1209, 4 -> 1202 TFLOP/s); otherwise two.
   constexpr int DEF_NP = Cfg::SHARE_S ? 1 : 2;
@@ -556,7 +584,7 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
                        : fa2_fwd_tcgen05_kernel<Cfg, false, P4, DEF_NP>;
   }
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), di.device, Cfg::SMEM_BYTES)) return rc;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, tbuf);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, int(N), scale_log2, tbuf, mask);
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;
 }
@@ -565,7 +593,21 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
 
 extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N,
                                  int64_t D, float scale, int v_is_dn, int variant, void* stream) {
+  return b200k_fa2_fwd(Q, K, V, O, B, H, N, D, scale, v_is_dn, B200K_F16, 0, nullptr, variant, stream);
+}
+
+extern "C" int b200k_fa2_fwd(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N,
+                             int64_t D, float scale, int v_is_dn, int dtype, int causal, const int* seqlens_k, int variant,
+                             void* stream) {
   using namespace b200k;
+  if (dtype != B200K_F16 && dtype != B200K_BF16)
+    return set_error(B200K_EDTYPE, "b200k_fa2_fwd: dtype %d not supported (f16, bf16)", dtype);
+  if (dtype == B200K_BF16 && v_is_dn)
+    return set_error(B200K_EARG, "b200k_fa2_fwd: the [B,H,D,N] V layout is built for fp16 only");
+  Fa2Mask mask;
+  mask.seqlens = seqlens_k;
+  mask.H = int(H);
+  mask.causal = causal ? 1 : 0;
   const bool trace = (variant & 0x100) != 0;  // debugging: cycle trace of CTA (0,0), see b200k_debug_set_trace
   // Experiment switches (round-robin measurements on one B200, profiles/r01_fa2_variants.txt and r01_fa2_*.log;
   // TFLOP/s at (4,48,8192,64) unless noted):
@@ -586,7 +628,7 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
   const int poly = poly_sel == 7 ? 0 : (poly_sel ? min(4, poly_sel) : ((variant & 0x800) ? 3 : 1));
   const int np_sel = (variant >> 12) & 3;  // 0 default, 1 -> 1 piece, 2 -> 2 pieces, 3 -> 4 pieces
   const int np = np_sel == 3 ? 4 : np_sel;  // 0 = the configuration's default
-  if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_fa2_fwd_f16: null pointer");
+  if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_fa2_fwd: null pointer");
   if (B < 1 || H < 1 || N < 1 || N > INT32_MAX || B * H > 65535)
     return set_error(B200K_ESHAPE, "b200k_fa2_fwd_f16: need B,H,N >= 1 and B*H <= 65535 (got B=%lld H=%lld N=%lld)",
                      (long long)B, (long long)H, (long long)N);
@@ -598,26 +640,35 @@ extern "C" int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, vo
   int rc = get_device_info(&di);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == B200K_BF16) {
+    const int p01 = poly ? 1 : 0;  // the bf16 builds exist with the production exp2 settings only
+    switch (D) {
+      case 32: return launch_fa2<Fa2Cfg<32, 128, 4, false, false, false, 1>>(Q, K, V, O, B, H, N, scale, s, di, 0, false, p01, mask);
+      case 64: return launch_fa2<Fa2Cfg<64, 128, 4, false, false, false, 1>>(Q, K, V, O, B, H, N, scale, s, di, 0, false, p01, mask);
+      case 96: return launch_fa2<Fa2Cfg<96, 64, 4, false, false, false, 1>>(Q, K, V, O, B, H, N, scale, s, di, 0, false, p01, mask);
+      default: return launch_fa2<Fa2Cfg<128, 128, 2, false, false, true, 1>>(Q, K, V, O, B, H, N, scale, s, di, 0, false, p01, mask);
+    }
+  }
   if (v_is_dn) {
     switch (D) {
-      case 32: return launch_fa2<Fa2Cfg<32, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
-      case 64: return launch_fa2<Fa2Cfg<64, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
-      case 96: return launch_fa2<Fa2Cfg<96, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
-      default: return launch_fa2<Fa2Cfg<128, 128, 2, true, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
+      case 32: return launch_fa2<Fa2Cfg<32, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly, mask);
+      case 64: return launch_fa2<Fa2Cfg<64, 128, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly, mask);
+      case 96: return launch_fa2<Fa2Cfg<96, 64, 4, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly, mask);
+      default: return launch_fa2<Fa2Cfg<128, 128, 2, true, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly, mask);
     }
   }
   switch (D) {
-    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
+    case 32: return launch_fa2<Fa2Cfg<32, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly, mask);
     case 64:
       if (variant & 0x20000)  // one shared S buffer (forced ping-pong of the two tiles) as for D = 128: 2 % slower here
-        return launch_fa2<Fa2Cfg<64, 128, 4, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly);
-      return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly);
-    case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly);
+        return launch_fa2<Fa2Cfg<64, 128, 4, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly, mask);
+      return launch_fa2<Fa2Cfg<64, 128, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly, mask);
+    case 96: return launch_fa2<Fa2Cfg<96, 64, 4>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly, mask);
     default:
       // 0x400: the older layout for D = 128 (P aliases S, S0 S1 O0 O1) instead of the shared S buffer
       if (variant & 0x400)
-        return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly);
-      return launch_fa2<Fa2Cfg<128, 128, 2, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly);
+        return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly, mask);
+      return launch_fa2<Fa2Cfg<128, 128, 2, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly, mask);
   }
 }
 

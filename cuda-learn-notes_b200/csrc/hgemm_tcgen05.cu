@@ -25,13 +25,24 @@
 namespace b200k {
 
 // DT: 0 = fp16, 1 = bf16 (both kind::f16, 16-bit output), 2 = tf32 (kind::tf32 on fp32 operands, fp32 output)
-template <int CG_, int BN_, bool B_MN_, int STAGES_, int DT_ = 0>
+// MT: 128-row accumulator blocks per CTA.  MT = 1: two accumulator buffers of BN columns, the epilogue of tile i runs
+// under the main loop of tile i+1.  MT = 2 (with CG = 2: a 512 x 256 pair tile): both 256-column accumulators of a tile
+// fill the 512 TMEM columns, every B stage is used by two MMAs, so a CTA takes in 48 KB of operands per 1024 tensor
+// cycles instead of 32 KB per 512 - a quarter less L2 -> SM traffic per flop.  On this power-limited part that traffic
+// is clock frequency: ncu on 8192^3 shows cuBLAS (nvjet 256x256 per CTA, same arrangement) moving 6.44 GB from L2 into
+// the SMs at 1.44 GHz where the 256 x 256 pair tile moves 8.61 GB at 1.32 GHz with a busier tensor pipe.
+template <int CG_, int BN_, bool B_MN_, int STAGES_, int DT_ = 0, int MT_ = 1, bool A_MN_ = false>
 struct GemmCfg {
+  // A_MN: A is stored transposed, [K,M] row-major (M contiguous) - the "NT" / "TT" BLAS cases.  Like an
+  // [K,N] B it is consumed in place as an MN-major UMMA operand: boxes of BK k-rows x 64 m-elements.
+  static constexpr bool A_MN = A_MN_;
   static constexpr int CG = CG_;
   static constexpr int BN = BN_;
   static constexpr bool B_MN = B_MN_;  // true: B is [K,N] row-major (N contiguous) = "NN"; false: B^T [N,K] = "TN"
   static constexpr int STAGES = STAGES_;
-  static constexpr int BM_CTA = 128;
+  static constexpr int MT = MT_;
+  static constexpr int NACC = 2 / MT_;  // accumulator buffers in flight
+  static constexpr int BM_CTA = 128 * MT_;
   static constexpr int BM = BM_CTA * CG;
   static constexpr int DT = DT_;
   static constexpr int ELEM = (DT_ == 2) ? 4 : 2;       // bytes per operand / output element
@@ -44,7 +55,9 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARP_BYTES = 2 * 32 * 128;  // two 32-row x 128-byte buffers per epilogue warp
   static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;  // two fp32 accumulator buffers
+  static constexpr int TMEM_COLS = 2 * BN;  // NACC buffers of MT accumulators of BN fp32 columns
+  static_assert(MT_ == 1 || MT_ == 2, "MT");
+  static_assert(!(A_MN_ && (MT_ != 1 || DT_ == 2)), "A^T storage is built for the 16-bit types and MT = 1");
   static constexpr int BAR_BYTES = 1024;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + BAR_BYTES + STAGES * STAGE_BYTES + EPI_BYTES;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
@@ -211,7 +224,13 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // all bytes of both CTAs are accounted on the leader's barrier
             if (leader) mbar_arrive_expect_tx(fb_local, 2 * Cfg::STAGE_BYTES);
             const uint32_t fb = mapa(fb_local, 0);
-            tma_load_2d_2sm(sa, &tmA, fb, k0, m0, policy_a);
+            if constexpr (Cfg::A_MN) {
+#pragma unroll
+              for (int j = 0; j < Cfg::BM_CTA / Cfg::ROW_ELEMS; ++j)
+                tma_load_2d_2sm(sa + j * Cfg::BK * 128, &tmA, fb, m0 + j * Cfg::ROW_ELEMS, k0, policy_a);
+            } else {
+              tma_load_2d_2sm(sa, &tmA, fb, k0, m0, policy_a);
+            }
             if constexpr (B_MN) {
 #pragma unroll
               for (int j = 0; j < Cfg::BN_CTA / Cfg::ROW_ELEMS; ++j)
@@ -221,7 +240,13 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           } else {
             mbar_arrive_expect_tx(fb_local, Cfg::STAGE_BYTES);
-            tma_load_2d(sa, &tmA, fb_local, k0, m0, policy_a);
+            if constexpr (Cfg::A_MN) {
+#pragma unroll
+              for (int j = 0; j < Cfg::BM_CTA / Cfg::ROW_ELEMS; ++j)
+                tma_load_2d(sa + j * Cfg::BK * 128, &tmA, fb_local, m0 + j * Cfg::ROW_ELEMS, k0, policy_a);
+            } else {
+              tma_load_2d(sa, &tmA, fb_local, k0, m0, policy_a);
+            }
             if constexpr (B_MN) {
 #pragma unroll
               for (int j = 0; j < Cfg::BN_CTA / Cfg::ROW_ELEMS; ++j)
@@ -240,9 +265,11 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
     // Whole warp convergent; tcgen05.mma / commit issued by one elected lane.
     if (leader) {
-      constexpr uint32_t idesc = make_idesc(Cfg::BM, BN, /*operand format: f16, bf16, tf32*/ Cfg::DT, /*a_mn=*/false, /*b_mn=*/B_MN);
+      constexpr uint32_t idesc = make_idesc(128 * CG, BN, /*operand format: f16, bf16, tf32*/ Cfg::DT, /*a_mn=*/Cfg::A_MN, /*b_mn=*/B_MN);
       // A: K-major, rows 128 B apart, 8-row groups 1024 B apart.
-      constexpr uint64_t a_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);
+      constexpr uint64_t a_hi = Cfg::A_MN ? make_smem_desc_hi(Cfg::BK * 128, 1024, kSwizzle128B)
+                                          : make_smem_desc_hi(16, 1024, kSwizzle128B);
+      constexpr uint32_t a_kstep = Cfg::A_MN ? uint32_t(Cfg::UMMA_K) * 128u : 32u;
       // B (TN): same K-major layout.  B (NN): MN-major, one 128 B row = 64 (32 for tf32) N-elements, 8 K-rows per
       // 1024 B atom (SBO), the next row-full of N-elements one TMA box (BK rows x 128 B) further (LBO).
       // A 32-bit MN-major operand uses the "128B swizzle, 32-byte atoms" layout (UMMA layout type 1, TMA
@@ -257,11 +284,11 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int it = 0;; ++it) {
         const WorkItem w = get_work(plan, cluster_id, num_clusters, num_tiles, num_kb, it);
         if (w.kind < 0) break;
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = it % Cfg::NACC;
+        const uint32_t acc_phase = (it / Cfg::NACC) & 1;
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::MT * BN;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
@@ -271,9 +298,12 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; ++k) {
-              const uint64_t adesc = smem_desc(a_hi, sa + k * 32);
               const uint64_t bdesc = smem_desc(b_hi, sb + k * b_kstep);
-              umma_ss<CG, (Cfg::DT == 2)>(d_tmem, adesc, bdesc, idesc, (kb > w.kb0 || k != 0) ? 1u : 0u);
+#pragma unroll
+              for (int mt = 0; mt < Cfg::MT; ++mt) {   // rows [mt*128, mt*128+128) of this CTA's A stage, same B
+                const uint64_t adesc = smem_desc(a_hi, sa + mt * (128 * 128) + k * a_kstep);
+                umma_ss<CG, (Cfg::DT == 2)>(d_tmem + mt * BN, adesc, bdesc, idesc, (kb > w.kb0 || k != 0) ? 1u : 0u);
+              }
             }
             if constexpr (CG == 2) umma_commit_2sm(bar_empty + 8 * stage, 0b11);
             else umma_commit(bar_empty + 8 * stage);
@@ -298,16 +328,16 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (w.kind < 0) break;
       int tm, tn;
       tile_coords(w.tile, tiles_m, tiles_n, group_m, &tm, &tn);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int row0 = tm * Cfg::BM + int(cta_rank) * Cfg::BM_CTA + int(q) * 32;
+      const int acc = it % Cfg::NACC;
+      const uint32_t acc_phase = (it / Cfg::NACC) & 1;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       // one chunk = 32 rows x 128 bytes of C per warp: 64 columns of 16-bit output or 32 columns of fp32
       constexpr int CC = Cfg::ROW_ELEMS;
       // stream-K: this warp's 32 x BN slice of a cluster's partial tile, stored as [chunk][16-byte unit][lane] so that
       // every warp-wide access is one contiguous 512-byte segment
-      constexpr int WARP_PARTIAL = 32 * BN;  // floats
+      constexpr int WARP_PARTIAL = 32 * BN * Cfg::MT;  // floats
+      constexpr int NCHUNK = Cfg::MT * (BN / CC);
       const size_t my_slot = (size_t(cluster_id) * CG + cta_rank) * 4 + q;
       if (w.kind == 2) {
         // finisher: wait until every writer of this tile has published this warp's slice (flag == epoch)
@@ -320,28 +350,22 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         __threadfence();
       }
-#pragma unroll 1
-      for (int c = 0; c < BN / CC; ++c) {
-        uint32_t r[CC];
-        const uint32_t taddr = tmem_addr(tmem_base, q * 32, acc * BN + c * CC);
+      // Two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is converted, staged and stored
+      // (an unpipelined loop exposed the full TMEM read latency eight times per 512 x 256 tile, which has no second
+      // accumulator buffer to hide its epilogue behind).
+      auto load_chunk = [&](int c, uint32_t* r) {
+        const uint32_t taddr = tmem_addr(tmem_base, q * 32, acc * Cfg::MT * BN + c * CC);
         tmem_ld_32x32b_x32(taddr, r);
         if constexpr (CC == 64) tmem_ld_32x32b_x32(taddr + 32, r + 32);
-        tmem_wait_ld();
-        if (c == BN / CC - 1) {
-          // accumulator fully read: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CG == 2) mbar_arrive_cluster(mapa(bar_tempty + 8 * acc, 0));
-            else mbar_arrive(bar_tempty + 8 * acc);
-          }
-        }
+      };
+      auto process_chunk = [&](int c, uint32_t* r) {
+        const int row0 = tm * Cfg::BM + int(cta_rank) * Cfg::BM_CTA + (c / (BN / CC)) * 128 + int(q) * 32;
         if (w.kind == 1) {
           // writer: raw fp32 partial sums to this cluster's workspace slot
           uint4* dst = reinterpret_cast<uint4*>(plan.partials + my_slot * WARP_PARTIAL) + size_t(c) * (CC / 4) * 32 + lane;
 #pragma unroll
           for (int j = 0; j < CC / 4; ++j) dst[j * 32] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          continue;
+          return;
         }
         if (w.kind == 2) {
           for (int cc = cluster_id + 1; cc <= w.last_writer; ++cc) {   // fixed order: deterministic sums
@@ -378,13 +402,35 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         fence_proxy_async_smem();
         __syncwarp();
-        const int col0 = tn * BN + c * CC;
+        const int col0 = tn * BN + (c % (BN / CC)) * CC;
         if (lane == 0) {
           // One bulk group per chunk, also for chunks that lie outside C (ragged N or M): the wait_read<1> above counts
           // groups, and an uncounted chunk would let the chunk after it overwrite a buffer whose store is still reading.
           if (row0 < M && col0 < N) tma_store_2d(&tmC, buf, col0, row0);
           tma_store_commit();
         }
+      };
+      auto release_tmem = [&]() {
+        // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(mapa(bar_tempty + 8 * acc, 0));
+          else mbar_arrive(bar_tempty + 8 * acc);
+        }
+      };
+      static_assert(NCHUNK % 2 == 0, "chunk pairs");
+      uint32_t ra[CC], rb[CC];
+      load_chunk(0, ra);
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; c += 2) {
+        tmem_wait_ld();            // chunk c is in ra
+        load_chunk(c + 1, rb);
+        process_chunk(c, ra);
+        tmem_wait_ld();            // chunk c+1 is in rb
+        if (c + 2 < NCHUNK) load_chunk(c + 2, ra);
+        else release_tmem();
+        process_chunk(c + 1, rb);
       }
       if (w.kind == 1) {
         // publish: all lanes' partial stores, then the flag (the finisher's matching warp polls it)
@@ -442,7 +488,9 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
                         const DeviceInfo& di, int tune) {
   CUtensorMap tmA, tmB, tmC;
   int rc;
-  if ((rc = make_tmap_2d(&tmA, A, M, K, K, Cfg::BM_CTA, Cfg::BK, Cfg::ELEM))) return rc;
+  if (Cfg::A_MN) rc = make_tmap_2d(&tmA, A, K, M, M, Cfg::BK, Cfg::ROW_ELEMS, Cfg::ELEM);
+  else rc = make_tmap_2d(&tmA, A, M, K, K, Cfg::BM_CTA, Cfg::BK, Cfg::ELEM);
+  if (rc) return rc;
   if (Cfg::B_MN) rc = make_tmap_2d(&tmB, B, K, N, N, Cfg::BK, Cfg::ROW_ELEMS, Cfg::ELEM, /*atom32=*/Cfg::DT == 2);
   else rc = make_tmap_2d(&tmB, B, N, K, K, Cfg::BN_CTA, Cfg::BK, Cfg::ELEM);
   if (rc) return rc;
@@ -458,10 +506,15 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   plan.trace = g_hgemm_trace;
   const int num_kb = int((K + Cfg::BK - 1) / Cfg::BK);
   const int64_t rem_tiles = num_tiles % max_clusters;
-  if (rem_tiles != 0 && num_kb >= 8 && max_clusters <= 128 && !((tune >> 20) & 1)) {
+  // Only when at least one data-parallel round follows: the finisher's fix-up (wait for the writers, read their partials
+  // back from L2) then runs under the next tile's main loop.  With nothing to hide behind it costs more than it saves
+  // (2048^3, 64 tiles on 74 pairs: 27.3 us stream-K vs 19.0 us plain, measured).
+  // Not with MT = 2 either: a single accumulator buffer means the finisher's fix-up stalls the MMA stream (8192^3:
+  // 701 us with the remainder round stream-K, 677 us without - ncu, profiles/r02_hgemm_tile_sweep_ncu.txt).
+  if (Cfg::NACC == 2 && rem_tiles != 0 && num_tiles > max_clusters && num_kb >= 8 && max_clusters <= 128 && !((tune >> 20) & 1)) {
     const int64_t units = rem_tiles * num_kb;
     SkWorkspace* ws = nullptr;
-    if ((rc = get_sk_workspace(di.device, stream, size_t(max_clusters) * Cfg::CG * 128 * Cfg::BN * sizeof(float), &ws))) return rc;
+    if ((rc = get_sk_workspace(di.device, stream, size_t(max_clusters) * Cfg::CG * Cfg::BM_CTA * Cfg::BN * sizeof(float), &ws))) return rc;
     clusters = max_clusters;
     plan.sk_tiles = int(rem_tiles);
     plan.units_lo = int(units / clusters);
@@ -504,7 +557,7 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
 namespace b200k {
 template <int DT>
 static int gemm_dispatch(const char* who, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,
-                         int b_is_nk, int variant, void* stream) {
+                         int b_is_nk, int variant, void* stream, int a_is_km = 0) {
   constexpr int PACK = (DT == 2) ? 4 : 8;  // elements per 16 bytes
   if (!A || !B || !C) return set_error(B200K_EARG, "%s: null pointer", who);
   if (M < 1 || N < 1 || K < 1 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
@@ -524,9 +577,23 @@ static int gemm_dispatch(const char* who, const void* A, const void* B, void* C,
     // 1-CTA 128x256 tile doubles the number of work units.  (The 256x128 pair tile is L2-bandwidth bound: measured
     // 0.59x of the 256x256 tile at 2048^3, profiles/r01_hgemm_bringup_check.jsonl.)
     const int64_t t256 = ((M + 255) / 256) * ((N + 255) / 256);
+    const int64_t t512 = ((M + 511) / 512) * ((N + 255) / 256);
     variant = (t256 * 4 >= di.sm_count) ? B200K_HGEMM_2CTA_256x256 : B200K_HGEMM_1CTA_128x256;
+    // 512 x 256 pair tiles once there are at least ~3 rounds of them (less operand traffic per flop: higher clocks under
+    // the power cap); tune bit 21 keeps the 256 x 256 tile (A/B measurements).
+    if (t512 * 2 >= 3 * di.sm_count && !((tune >> 21) & 1)) variant = B200K_HGEMM_2CTA_512x256;
   }
   const bool nn = (b_is_nk == 0);
+  if (a_is_km) {
+    // A^T storage: one build (256 x 256 pair tile), 16-bit types
+    if constexpr (DT == 2) {
+      return set_error(B200K_EDTYPE, "%s: A stored as [K,M] is built for f16 / bf16 only", who);
+    } else {
+      if (M % PACK) return set_error(B200K_ESHAPE, "%s: M must be a multiple of %d when A is stored as [K,M]", who, PACK);
+      return nn ? launch_hgemm<GemmCfg<2, 256, true, 6, DT, 1, true>>(A, B, C, M, N, K, s, di, tune)
+                : launch_hgemm<GemmCfg<2, 256, false, 6, DT, 1, true>>(A, B, C, M, N, K, s, di, tune);
+    }
+  }
   switch (variant) {
     case B200K_HGEMM_1CTA_128x256:
       return nn ? launch_hgemm<GemmCfg<1, 256, true, 4, DT>>(A, B, C, M, N, K, s, di, tune)
@@ -534,6 +601,9 @@ static int gemm_dispatch(const char* who, const void* A, const void* B, void* C,
     case B200K_HGEMM_2CTA_256x256:
       return nn ? launch_hgemm<GemmCfg<2, 256, true, 6, DT>>(A, B, C, M, N, K, s, di, tune)
                 : launch_hgemm<GemmCfg<2, 256, false, 6, DT>>(A, B, C, M, N, K, s, di, tune);
+    case B200K_HGEMM_2CTA_512x256:
+      return nn ? launch_hgemm<GemmCfg<2, 256, true, 4, DT, 2>>(A, B, C, M, N, K, s, di, tune)
+                : launch_hgemm<GemmCfg<2, 256, false, 4, DT, 2>>(A, B, C, M, N, K, s, di, tune);
     case B200K_HGEMM_2CTA_256x128:
       return nn ? launch_hgemm<GemmCfg<2, 128, true, 8, DT>>(A, B, C, M, N, K, s, di, tune)
                 : launch_hgemm<GemmCfg<2, 128, false, 8, DT>>(A, B, C, M, N, K, s, di, tune);
@@ -554,6 +624,16 @@ extern "C" int b200k_debug_set_hgemm_trace(void* dev_u64_buffer) {
 extern "C" int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk,
                                int variant, void* stream) {
   return b200k::gemm_dispatch<0>("b200k_hgemm_f16", A, B, C, M, N, K, b_is_nk, variant, stream);
+}
+
+extern "C" int b200k_gemm_ex(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int a_is_km, int b_is_nk,
+                             int dtype, int variant, void* stream) {
+  switch (dtype) {
+    case B200K_F16: return b200k::gemm_dispatch<0>("b200k_gemm_ex(f16)", A, B, C, M, N, K, b_is_nk, variant, stream, a_is_km);
+    case B200K_BF16: return b200k::gemm_dispatch<1>("b200k_gemm_ex(bf16)", A, B, C, M, N, K, b_is_nk, variant, stream, a_is_km);
+    case B200K_F32: return b200k::gemm_dispatch<2>("b200k_gemm_ex(tf32)", A, B, C, M, N, K, b_is_nk, variant, stream, a_is_km);
+    default: return b200k::set_error(B200K_EDTYPE, "b200k_gemm_ex: dtype %d not supported (f16, bf16, f32-as-tf32)", dtype);
+  }
 }
 
 extern "C" int b200k_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk, int dtype,

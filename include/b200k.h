@@ -54,6 +54,7 @@ int b200k_device_info(int* sm_count, int* cc_major, int* cc_minor);
 #define B200K_HGEMM_1CTA_128x256 1
 #define B200K_HGEMM_2CTA_256x256 2
 #define B200K_HGEMM_2CTA_256x128 3
+#define B200K_HGEMM_2CTA_512x256 4 /* 256 x 256 per CTA: both accumulators of a tile fill TMEM, 25 % less L2 -> SM traffic per flop */
 int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk,
                     int variant, void* stream);
 
@@ -65,6 +66,11 @@ int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N,
  * "128B swizzle with 32-byte atoms" shared-memory layout (TMA SWIZZLE_128B_ATOM_32B, UMMA layout type 1). */
 int b200k_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk, int dtype, int variant,
                void* stream);
+/* All four storage cases (SURVEY.md 8(f)-4 "TN/NT"): a_is_km != 0 means A is stored transposed, [K,M] row-major (the BLAS
+ * "NT" / "TT" cases; f16 and bf16; M % 8 == 0); b_is_nk as above.  Operands are consumed in place (MN-major UMMA
+ * descriptors), no transpose pass.  b200k_gemm(...) == b200k_gemm_ex(..., a_is_km = 0, ...). */
+int b200k_gemm_ex(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int a_is_km, int b_is_nk, int dtype,
+                  int variant, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ attention
  * O = softmax(Q K^T * scale) V, non-causal, Q/K/V/O [B,H,N,D] fp16 contiguous (V optionally [B,H,D,N]).
@@ -87,6 +93,14 @@ int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, void* O, int6
                       int64_t D, float scale, int v_is_dn, int variant, void* stream);
 int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N,
                        int64_t D, float scale, int variant, void* stream);
+/* b200k_fa2_fwd — the same FA-2 kernel with the caller-facing options the reference lacks:
+ *   dtype      B200K_F16 or B200K_BF16 (Q, K, V, O and the P operand; statistics and accumulators stay fp32)
+ *   causal     != 0: query row r attends keys <= r; KV tiles above the diagonal are skipped, not masked
+ *   seqlens_k  NULL, or int32 device array [B]: keys >= seqlens_k[b] are masked for batch b (key-padding mask of the
+ *              padded [B,H,N,D] layout; 1 <= seqlens_k[b] <= N; every query row is still computed)
+ * b200k_fa2_fwd_f16(...) == b200k_fa2_fwd(..., B200K_F16, 0, NULL, ...). */
+int b200k_fa2_fwd(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N, int64_t D,
+                  float scale, int v_is_dn, int dtype, int causal, const int* seqlens_k, int variant, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ support kernels
  * HBM-roofline kernels (128-bit vectorised, warp-shuffle reductions, no tensor cores).  dtype enums: */

@@ -49,16 +49,26 @@ def hgemm_f16acc_k16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float | None = None) -> torch.Tensor:
-    """O = softmax(Q K^T * scale) V in fp32, rounded once to fp16: `unfused_standard_attn`
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float | None = None, causal: bool = False,
+              seqlens=None) -> torch.Tensor:
+    """O = softmax(Q K^T * scale) V in fp32, rounded once to the input dtype: `unfused_standard_attn`
     (kernels/flash-attn/flash_attn_mma.py:L384-388); scale = 1/sqrt(D) as hard-coded by both references
-    (flash_attn_mma_share_qkv.cu:L95, ffpa-attn-mma/csrc/cuffpa/launch_templates.cuh:L320)."""
+    (flash_attn_mma_share_qkv.cu:L95, ffpa-attn-mma/csrc/cuffpa/launch_templates.cuh:L320).
+    The reference has no masks; `causal` (row r sees keys <= r) and `seqlens` (per-batch count of valid keys, a
+    key-padding mask) restate the textbook definitions for the SURVEY 8(f)-4 options of b200k_fa2_fwd."""
     q32, k32, v32 = q.float().cpu(), k.float().cpu(), v.float().cpu()
     if scale is None:
         scale = 1.0 / math.sqrt(q.shape[-1])
     s = (q32 @ k32.transpose(-1, -2)) * scale
+    N = q.shape[-2]
+    if causal:
+        keep = torch.ones(N, N, dtype=torch.bool).tril()
+        s = s.masked_fill(~keep, float("-inf"))
+    if seqlens is not None:
+        sl = torch.as_tensor(seqlens).cpu().long().view(-1, 1, 1, 1)
+        s = s.masked_fill(torch.arange(N).view(1, 1, 1, N) >= sl, float("-inf"))
     p = torch.softmax(s, dim=-1)
-    return (p @ v32).half()
+    return (p @ v32).to(q.dtype if q.dtype in (torch.float16, torch.bfloat16) else torch.float16)
 
 
 def attention_tiled(q, k, v, Bc: int = 64, pv_acc_f16: bool = False, o_store_f16: bool = False,

@@ -146,3 +146,95 @@ def test_full_size_properties(shape):
         rows = torch.tensor([0, 1, N // 2 + 3, N - 1], device="cuda")
         ref = oracle.attention(q[b, h, rows][None, None], k[b, h][None, None], v1[b, h][None, None])[0, 0]
         assert torch.allclose(o1[b, h, rows].cpu().float(), ref.float(), **TOL)
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8(f)-4 options
+@pytest.mark.parametrize("shape", [(1, 2, 256, 64), (2, 3, 1000, 64), (1, 2, 513, 128), (1, 1, 77, 32), (1, 2, 640, 96),
+                                   (1, 1, 1, 64), (1, 2, 2048, 128), (1, 1, 255, 64), (1, 1, 257, 64)])
+def test_causal_mask_vs_oracle_and_sdpa(shape):
+    from b200k import ops
+
+    B, H, N, D = shape
+    torch.manual_seed(N * 3 + D)
+    q, k, v = [torch.randn(B, H, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.full_like(q, float("nan"))
+    ops.fa2_fwd(q, k, v, o, causal=True)
+    assert torch.isfinite(o).all()
+    assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v, causal=True).float(), **TOL)
+    sd = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True)
+    assert torch.allclose(o.float(), sd.float(), **TOL)
+    # row 0 sees only key 0: O[0] == V[0] exactly (softmax of one element, fp16 round trip of V)
+    assert torch.equal(o[:, :, 0], v[:, :, 0])
+
+
+@pytest.mark.parametrize("shape,lens", [((3, 2, 512, 64), [512, 100, 1]), ((2, 2, 1000, 128), [999, 129]),
+                                        ((2, 1, 300, 32), [300, 37])])
+@pytest.mark.parametrize("causal", [False, True])
+def test_key_padding_seqlens_vs_oracle(shape, lens, causal):
+    from b200k import ops
+
+    B, H, N, D = shape
+    torch.manual_seed(N + D + causal)
+    q, k, v = [torch.randn(B, H, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    sl = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    o = torch.full_like(q, float("nan"))
+    ops.fa2_fwd(q, k, v, o, causal=causal, seqlens_k=sl)
+    want = oracle.attention(q, k, v, causal=causal, seqlens=lens).float()
+    assert torch.isfinite(o).all()
+    assert torch.allclose(o.cpu().float(), want, **TOL)
+    # keys past the length must not influence anything: poison them and recompute
+    k2, v2 = k.clone(), v.clone()
+    for b, n in enumerate(lens):
+        k2[b, :, n:] = 1e4
+        v2[b, :, n:] = -1e4
+    o2 = torch.empty_like(o)
+    ops.fa2_fwd(q, k2, v2, o2, causal=causal, seqlens_k=sl)
+    assert torch.equal(o, o2)
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 256, 64), (2, 2, 1000, 128), (1, 2, 333, 32), (1, 2, 512, 96), (1, 4, 4096, 64)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_bf16_attention_vs_oracle(shape, causal):
+    """bf16 Q/K/V/O and P: fp32 statistics and accumulators; P and O carry bf16's 2^-9 relative rounding."""
+    from b200k import ops
+
+    B, H, N, D = shape
+    torch.manual_seed(N + D)
+    q, k, v = [torch.randn(B, H, N, D, device="cuda").bfloat16() for _ in range(3)]
+    o = torch.full_like(q, float("nan"))
+    ops.fa2_fwd(q, k, v, o, causal=causal)
+    want = oracle.attention(q, k, v, causal=causal).float()
+    assert o.dtype == torch.bfloat16 and torch.isfinite(o).all()
+    # tolerance: the north star's rtol with bf16's 8x coarser mantissa: rtol 1e-2 -> 2e-2, atol 1e-3 -> 8e-3 / sqrt(keys) scale
+    assert torch.allclose(o.cpu().float(), want, rtol=2e-2, atol=4e-3)
+    sd = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal)
+    assert (o.float() - want.cuda()).abs().max() <= 2.0 * (sd.float() - want.cuda()).abs().max() + 2e-3
+
+
+def test_causal_config3_full_size_properties():
+    """(4,48,8192,64) causal: sampled rows against an fp32 reference on the GPU, and tile skipping must not change rows."""
+    from b200k import ops
+
+    B, H, N, D = 2, 8, 8192, 64
+    torch.manual_seed(8)
+    q, k, v = [torch.randn(B, H, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.empty_like(q)
+    ops.fa2_fwd(q, k, v, o, causal=True)
+    rows = torch.tensor([0, 1, 127, 128, 255, 256, 4095, 4096, 8191], device="cuda")
+    s = (q[:, :, rows].float() @ k.float().transpose(-1, -2)) / D ** 0.5
+    s = s.masked_fill(torch.arange(N, device="cuda").view(1, 1, 1, N) > rows.view(1, 1, -1, 1), float("-inf"))
+    want = torch.softmax(s, -1) @ v.float()
+    assert torch.allclose(o[:, :, rows].float(), want, **TOL)
+    # the first 1024 rows only depend on the first 1024 keys: a shorter problem gives the same bits
+    o2 = torch.empty(B, H, 1024, D, dtype=torch.half, device="cuda")
+    ops.fa2_fwd(q[:, :, :1024].contiguous(), k[:, :, :1024].contiguous(), v[:, :, :1024].contiguous(), o2, causal=True)
+    assert torch.equal(o2, o[:, :, :1024])
+
+
+@pytest.mark.parametrize("D", [192, 256, 320, 384, 448, 512, 576, 640, 704, 768, 832, 896, 960, 1024])
+def test_ffpa_every_ladder_rung(D):
+    """Every head dim of the reference's ladder (ffpa-attn-mma/csrc/cuffpa/launch_templates.cuh:L529-551), ragged N."""
+    torch.manual_seed(D)
+    q, k, v = [torch.randn(1, 2, 300, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = _run(q, k, v)
+    assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), **TOL)

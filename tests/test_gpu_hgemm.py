@@ -70,7 +70,10 @@ def test_hgemm_drop_in_names_route_to_kernel():
 @pytest.mark.parametrize("n", [2048, 4096, 8192])
 def test_hgemm_full_size_sampled_entries_and_linearity(n):
     """BASELINE config #2 sizes: (1) 512 sampled entries against fp64 dot products of the same fp16 inputs,
-    (2) structure: C(A, [B1 | B2]) column blocks equal C(A, B1), C(A, B2) bit for bit (tiles are independent)."""
+    (2) structure: C(A, [B1 | B2]) column blocks equal C(A, B1), C(A, B2): tiles are independent.  Bit for bit with the
+    stream-K remainder round off (variant bit 20); with it on, which tiles are split along K depends on the tile count,
+    so the fp32 partial sums of those tiles are added in a different (fixed) order: equal within one fp16 ulp, and the
+    result is still deterministic run to run."""
     from b200k import ops
 
     torch.manual_seed(n)
@@ -83,9 +86,19 @@ def test_hgemm_full_size_sampled_entries_and_linearity(n):
     got = c[idx[:, 0], idx[:, 1]].double()
     assert torch.allclose(got, want, **_tol(n))
     half = n // 2
+    bh = b[:, :half].contiguous()
     c1 = torch.empty(n, half, dtype=torch.half, device="cuda")
-    ops.hgemm(a, b[:, :half].contiguous(), c1)
-    assert torch.equal(c1, c[:, :half])
+    ops.hgemm(a, bh, c1)
+    # one fp16 ulp of the value; near zero the fp32 summation-order difference (~ sqrt(K) * 2^-24 per add) dominates
+    assert torch.allclose(c1.float(), c[:, :half].float(), rtol=2.0 ** -10, atol=2e-3)
+    assert (c1 == c[:, :half]).float().mean() > 0.99
+    c2 = torch.empty_like(c)
+    ops.hgemm(a, b, c2)
+    assert torch.equal(c2, c)                                                               # deterministic
+    SK_OFF = 2 | (1 << 20)      # 2-CTA 256x256 tile, stream-K off
+    ops.hgemm(a, b, c2, variant=SK_OFF)
+    ops.hgemm(a, bh, c1, variant=SK_OFF)
+    assert torch.equal(c1, c2[:, :half])                                                    # tiles independent, bit for bit
 
 
 def test_hgemm_16384_smoke_and_stream():
@@ -177,3 +190,28 @@ def test_ragged_n_epilogue_staging_buffers(dtype):
             c = torch.full((M, N), float("nan"), device="cuda").to(dtype)
             ops.gemm(a, b, c)
             assert ((c.double().cpu() - want).abs() <= tol * mag + 1e-30).all(), (dtype, M, N, K, rep)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("tn", [False, True])
+@pytest.mark.parametrize("shape", [(256, 256, 256), (1024, 512, 768), (264, 520, 200), (2048, 2048, 2048), (4096, 4096, 1024)])
+def test_gemm_a_stored_transposed_nt_tt(shape, tn, dtype):
+    """A stored as [K,M] ("NT"; with tn also "TT"), consumed in place as an MN-major operand."""
+    from b200k import ops
+
+    M, N, K = shape
+    torch.manual_seed(M + N + K)
+    at = torch.randn(K, M, device="cuda").to(dtype)          # storage of A^T
+    b = torch.randn(K, N, device="cuda").to(dtype)
+    c = torch.full((M, N), float("nan"), device="cuda").to(dtype)
+    bb = b.t().contiguous().t() if tn else b
+    ops.gemm(at.t(), bb, c, tn=tn, a_km=True)
+    want = at.t().double() @ b.double()
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    assert torch.isfinite(c).all()
+    assert (c.double() - want).abs().max() <= want.abs().max() * eps
+    # same numbers as the NN call on a materialised A
+    c2 = torch.empty_like(c)
+    ops.gemm(at.t().contiguous(), b, c2, variant=2 | (1 << 20))
+    ops.gemm(at.t(), bb, c, tn=tn, a_km=True, variant=2 | (1 << 20))
+    assert torch.equal(c, c2)

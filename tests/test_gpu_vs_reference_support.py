@@ -121,6 +121,15 @@ def test_softmax_all_11(ref_exports):
         for name in ref_exports["softmax_lib"]:
             if "per_token" not in name:
                 continue
+            # REFERENCE BUG (found by running it on sm_100a): both online-softmax kernels read `shared[local_tid]` for
+            # local_tid < 32 from a `__shared__ MD shared[NUM_THREADS/32]` array (softmax.cu:L326-334, L366-374) - an
+            # out-of-bounds shared-memory read whenever the block has fewer than 32 warps.  On B200 it raises
+            # "illegal memory access" at H = 256 (the script's first shape) and takes the CUDA context with it, so the
+            # reference is only called where its block has exactly 32 warps: H = 1024 (f32) and H = 4096 (f32x4_pack).
+            if name == "online_safe_softmax_f32_per_token" and H != 1024:
+                continue
+            if name == "online_safe_softmax_f32x4_pack_per_token" and H != 4096:
+                continue
             x = x32.half() if "f16" in name else x32
             y_ref, y = torch.zeros_like(x), torch.zeros_like(x)
             if _try_ref(getattr(ref, name), x, y_ref) is None or not torch.isfinite(y_ref).all() or float(y_ref.sum()) == 0:
@@ -236,8 +245,16 @@ def test_activations_with_reference_clamps(ref_exports, op):
                 # fast-math expf / tanhf in the reference vs ex2.approx here
                 assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-5), (name, (y - y_ref).abs().max().item())
             else:
-                # the reference computes in half (hexp, __hdiv): a few fp16 ulps
-                assert torch.allclose(y.float(), y_ref.float(), rtol=1e-2, atol=2e-3), (name, (y.float() - y_ref.float()).abs().max().item())
+                # the reference computes in half (hexp, __hdiv): a few fp16 ulps.
+                # REFERENCE DEFECT (gelu f16 only): tanh is formed as (e - 1) / (e + 1) with e = hexp(2 * inner) in half
+                # (gelu.cu:L44-50); e overflows to inf for x > ~4.03 (2 * inner > 11.09) and inf / inf = NaN, although
+                # the input clamp suggests otherwise.  The product returns the finite limit there (y = x).  Compare where
+                # the reference is finite, and check that its NaNs are exactly that region.
+                ok = torch.isfinite(y_ref)
+                if not bool(ok.all()):
+                    assert op == "gelu" and float(x[~ok].float().min()) > 4.0, name
+                    assert torch.isfinite(y).all() and torch.allclose(y[~ok].float(), x[~ok].float().clamp(max=11.09), rtol=1e-2), name
+                assert torch.allclose(y[ok].float(), y_ref[ok].float(), rtol=1e-2, atol=2e-3), (name, (y[ok].float() - y_ref[ok].float()).abs().max().item())
 
 
 def test_layer_norm_all_8(ref_exports):
