@@ -63,8 +63,8 @@ struct Fa2Cfg {
   static constexpr int KV_TILE_BYTES = NCH * KV_CHUNK_BYTES;  // = BC * D * 2 (also for the transposed-V layout)
   static constexpr int BAR_BYTES = 1024;
   static constexpr int SMEM_BYTES = 1024 + BAR_BYTES + 2 * Q_TILE_BYTES + 2 * STAGES * KV_TILE_BYTES;
-  static constexpr int S_COL0 = 0, S_COL1 = SHARE_S ? 0 : BC;
   static constexpr int NS = SHARE_S ? 1 : 2;           // S buffers
+  static constexpr int S_COL0 = 0, S_COL1 = SHARE_S ? 0 : BC;
   static constexpr int P_COL0 = ALIAS_P ? S_COL0 : NS * BC, P_COL1 = ALIAS_P ? S_COL1 : NS * BC + BC / 2;
   static constexpr int O_COL0 = ALIAS_P ? 2 * BC : (NS + 1) * BC, O_COL1 = O_COL0 + D;
   static constexpr int TMEM_COLS = 512;
@@ -94,7 +94,7 @@ struct Fa2Mask {
   int causal = 0;
 };
 
-template <class Cfg, bool TRACE, int POLY, int NP>
+template <class Cfg, bool TRACE, int POLY, int NP, bool MASKED = false>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int N,
@@ -118,8 +118,8 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t bar_v_full = bar_k_empty + 8 * STAGES;   // STAGES
   const uint32_t bar_v_empty = bar_v_full + 8 * STAGES;   // STAGES
   const uint32_t bar_s_full = bar_v_empty + 8 * STAGES;   // 2   S_i(j) ready                 (MMA -> softmax i)
-  const uint32_t bar_s_free = bar_s_full + 16;            // 2   S_i(j) is in registers       (softmax i -> MMA)
-  const uint32_t bar_p_full = bar_s_free + 16;            // 2x4 piece p of P_i(j) written (and O_i rescaled) (softmax i -> MMA)
+  const uint32_t bar_s_free = bar_s_full + 32;            // 2   S_i(j) is in registers       (softmax i -> MMA)
+  const uint32_t bar_p_full = bar_s_free + 32;            // 2x4 piece p of P_i(j) written (and O_i rescaled) (softmax i -> MMA)
   const uint32_t bar_p_free = bar_p_full + 64;            // 2   PV_i(j) done: P_i free, O_i stable (MMA -> softmax i)
   const uint32_t bar_o_full = bar_p_free + 16;            // 2   last PV_i done               (MMA -> softmax i)
   const uint32_t tmem_slot = bar_o_full + 16;
@@ -132,21 +132,26 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
+  // The masked build is a separate instantiation: the extra live values cost the unmasked D = 128 kernel (168 registers,
+  // the cap at 384 threads) 56 bytes of spills and ~8 % when they were runtime flags of one kernel.
+  const bool causal = MASKED && mask.causal;
   // causal: CTAs near the end of the sequence have the most KV tiles; start them first
-  const int q0 = (mask.causal ? int(gridDim.x - 1 - blockIdx.x) : int(blockIdx.x)) * 256;
-  const int n_keys = mask.seqlens ? min(N, max(1, mask.seqlens[bh / mask.H])) : N;  // valid keys of this batch
+  const int q0 = (causal ? int(gridDim.x - 1 - blockIdx.x) : int(blockIdx.x)) * 256;
+  const int n_keys = (MASKED && mask.seqlens) ? min(N, max(1, mask.seqlens[bh / mask.H])) : N;  // valid keys of this batch
   const int Tk = (n_keys + BC - 1) / BC;
-  const int T = mask.causal ? min(Tk, (q0 + 256 + BC - 1) / BC) : Tk;  // KV tiles this CTA walks
+  const int T = causal ? min(Tk, (q0 + 256 + BC - 1) / BC) : Tk;  // KV tiles this CTA walks
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_q_full + 8 * i, 1);
+    for (int i = 0; i < 4; ++i) {
       mbar_init(bar_s_full + 8 * i, 1);
       mbar_init(bar_s_free + 8 * i, 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_q_full + 8 * i, 1);
       for (int p = 0; p < 4; ++p) mbar_init(bar_p_full + 32 * i + 8 * p, 4);
       mbar_init(bar_p_free + 8 * i, 1);
       mbar_init(bar_o_full + 8 * i, 1);
@@ -374,22 +379,9 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t o_tmem = tmem_base + lane_base + (i ? Cfg::O_COL1 : Cfg::O_COL0);
     float m_ref = -INFINITY;  // reference max, in log2-scaled units
     float l = 0.f;
-    for (int j = 0; j < T; ++j) {
-      mbar_wait(bar_s_full + 8 * i, j & 1);
+    // one KV tile of this row: scores in sr (fp32 bits) -> P (packed 16-bit pairs, in place) -> TMEM, statistics updated
+    auto softmax_tile = [&](const int j, uint32_t* sr) {
       const bool tw = TRACE && lane == 0 && q == 0;  // one thread per warpgroup writes the trace
-      if (tw) tr(1 + i, j, 0);
-      tc_fence_after();
-      uint32_t sr[BC];
-#pragma unroll
-      for (int c = 0; c < BC / 32; ++c) tmem_ld_32x32b_x32(s_tmem + c * 32, sr + c * 32);
-      tmem_wait_ld();
-      if (tw) tr(1 + i, j, 1);
-      // the scores are in registers: give the S columns back so that S(j+1) is computed under this softmax
-      if constexpr (!Cfg::ALIAS_P) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_s_free + 8 * i);
-      }
       float* s = reinterpret_cast<float*>(sr);
       if (j == Tk - 1 && (n_keys % BC) != 0) {
         // ragged last tile only.  The empty asm keeps this a real (warp-uniform) branch: if-converted, the 2 x BC
@@ -400,7 +392,7 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int c = 0; c < BC; ++c)
           if (c >= valid) s[c] = -INFINITY;
       }
-      if (mask.causal && (j + 1) * BC - 1 > q0 + i * 128 + int(q) * 32) {
+      if (MASKED && causal && (j + 1) * BC - 1 > q0 + i * 128 + int(q) * 32) {
         // this KV tile reaches past the diagonal for some row of the warp (warp-uniform test on the warp's first row)
         asm volatile("" ::: "memory");
         const int last = q0 + i * 128 + int(q) * 32 + int(lane) - j * BC;  // last visible key of this row, tile-relative
@@ -489,6 +481,24 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
       if (tw) tr(1 + i, j, 6);
+    };
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(bar_s_full + 8 * i, j & 1);
+      const bool tw = TRACE && lane == 0 && q == 0;
+      if (tw) tr(1 + i, j, 0);
+      tc_fence_after();
+      uint32_t sr[BC];
+#pragma unroll
+      for (int c = 0; c < BC / 32; ++c) tmem_ld_32x32b_x32(s_tmem + c * 32, sr + c * 32);
+      tmem_wait_ld();
+      if (tw) tr(1 + i, j, 1);
+      // the scores are in registers: give the S columns back so that S(j+1) is computed under this softmax
+      if constexpr (!Cfg::ALIAS_P) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_s_free + 8 * i);
+      }
+      softmax_tile(j, sr);
     }
     // ---- epilogue: O_i / l -> fp16 -> swizzled smem (reusing this tile's Q buffer) -> TMA store
     mbar_wait(bar_o_full + 8 * i, 0);
@@ -570,7 +580,9 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
   constexpr int NPA = kLab ? (DEF_NP == 1 ? 2 : 1) : DEF_NP, NPB = kLab ? 4 : DEF_NP;  // the two non-default counts
   constexpr bool TR = kLab;
   if (np == 0) np = DEF_NP;
-  if (trace && g_fa2_trace && kLab) {
+  if (mask.causal || mask.seqlens) {
+    kern = poly ? fa2_fwd_tcgen05_kernel<Cfg, false, 1, DEF_NP, true> : fa2_fwd_tcgen05_kernel<Cfg, false, 0, DEF_NP, true>;
+  } else if (trace && g_fa2_trace && kLab) {
     tbuf = g_fa2_trace;
     kern = poly ? fa2_fwd_tcgen05_kernel<Cfg, TR, 1, DEF_NP> : fa2_fwd_tcgen05_kernel<Cfg, TR, 0, DEF_NP>;
   } else if (np != DEF_NP && kLab) {

@@ -511,7 +511,9 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   // (2048^3, 64 tiles on 74 pairs: 27.3 us stream-K vs 19.0 us plain, measured).
   // Not with MT = 2 either: a single accumulator buffer means the finisher's fix-up stalls the MMA stream (8192^3:
   // 701 us with the remainder round stream-K, 677 us without - ncu, profiles/r02_hgemm_tile_sweep_ncu.txt).
-  if (Cfg::NACC == 2 && rem_tiles != 0 && num_tiles > max_clusters && num_kb >= 8 && max_clusters <= 128 && !((tune >> 20) & 1)) {
+  const bool force_sk = ((tune >> 22) & 1) != 0;   // experiments: stream-K also for a single partial round
+  if (Cfg::NACC == 2 && rem_tiles != 0 && (num_tiles > max_clusters || force_sk) && num_kb >= 8 && max_clusters <= 128 &&
+      !((tune >> 20) & 1)) {
     const int64_t units = rem_tiles * num_kb;
     SkWorkspace* ws = nullptr;
     if ((rc = get_sk_workspace(di.device, stream, size_t(max_clusters) * Cfg::CG * Cfg::BM_CTA * Cfg::BN * sizeof(float), &ws))) return rc;

@@ -139,14 +139,23 @@ def test_softmax_all_11(ref_exports):
             tol = dict(rtol=1e-2, atol=1e-3) if x.dtype == torch.float16 else dict(rtol=2e-5, atol=1e-8)
             assert torch.allclose(y.float(), y_ref.float(), **tol), (name, S, H)
             ran.add(name)
-    # whole-tensor softmax over a flat vector (softmax.py:L60-66): grid-wide sum through a fence + atomicAdd
+    # whole-tensor softmax over a flat vector (softmax.py:L60-66).
+    # REFERENCE DEFECT: softmax_f32 / softmax_f32x4 add each block's sum to `total` with atomicAdd, execute __threadfence()
+    # and immediately divide by *total (softmax.cu:L109-116, L135-145).  A fence is not a grid barrier: a block divides by
+    # whatever partial total it happens to see, so the reference's output depends on block scheduling (observed on B200:
+    # softmax_f32x4 differs from the true softmax by more than 2e-5 relative) and can only be too LARGE (partial <= total).
+    # The product computes the true softmax (deterministic two-level sum, then one scaling pass); it is pinned to the
+    # exact result, and the reference is checked to be >= it, element by element.
     torch.manual_seed(1)
     x = torch.randn(128 * 128, device="cuda")
+    exact = torch.softmax(x.double(), 0)
     for name in ("softmax_f32", "softmax_f32x4"):
         y_ref, y = torch.zeros_like(x), torch.zeros_like(x)
         getattr(ref, name)(x, y_ref)
         getattr(ours, name)(x, y)
-        assert torch.allclose(y, y_ref, rtol=2e-5, atol=1e-10), name
+        assert torch.allclose(y.double(), exact, rtol=2e-6, atol=0.0), name
+        assert bool((y_ref.double() >= exact * (1 - 1e-5)).all()), name
+        assert abs(float(y.double().sum()) - 1.0) < 1e-5
         ran.add(name)
     assert ran == set(ref_exports["softmax_lib"]), set(ref_exports["softmax_lib"]) - ran
 

@@ -1,0 +1,85 @@
+"""Round-2 FA-2 experiments on the B200 box: correctness of the experiment builds against the default build and the
+oracle, then round-robin timing on BASELINE config #3.  Output: gpurun_out/r2/fa2_r2.jsonl"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "cuda-learn-notes_b200"))
+sys.path.insert(0, ROOT)
+import torch
+from b200k import ops
+from oracle import oracle
+
+OUT = os.path.join(ROOT, "gpurun_out", "r2")
+os.makedirs(OUT, exist_ok=True)
+VARIANTS = {"default": 0, "pf_bc64": 0x40000, "bc64": 0x80000, "pf_bc64_nopoly": 0x40000 | (7 << 14), "default_nopoly": 7 << 14,
+            "pf_bc64_np1": 0x40000 | (1 << 12)}
+
+
+def emit(rec, f):
+    print(json.dumps(rec), flush=True)
+    f.write(json.dumps(rec) + "\n")
+    f.flush()
+
+
+def timeit(fn, iters):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def check(f, D=64):
+    for shape in [(1, 2, 256, D), (1, 1, 64, D), (1, 1, 65, D), (2, 3, 1000, D), (1, 1, 1, D), (1, 2, 128, D), (1, 2, 192, D),
+                  (1, 1, 333, D), (1, 4, 2048, D)]:
+        torch.manual_seed(shape[2])
+        q, k, v = [torch.randn(*shape, dtype=torch.half, device="cuda") for _ in range(3)]
+        want = oracle.attention(q, k, v).float()
+        wantc = oracle.attention(q, k, v, causal=True).float()
+        for name, var in VARIANTS.items():
+            o = torch.full_like(q, float("nan"))
+            ops.fa2_fwd(q, k, v, o, variant=var)
+            oc = torch.full_like(q, float("nan"))
+            ops.fa2_fwd(q, k, v, oc, variant=var, causal=True)
+            torch.cuda.synchronize()
+            ok = bool(torch.allclose(o.cpu().float(), want, rtol=1e-2, atol=1e-3)) and bool(torch.allclose(oc.cpu().float(), wantc, rtol=1e-2, atol=1e-3))
+            emit({"what": "check", "shape": list(shape), "variant": name, "ok": ok,
+                  "max_err": float((o.cpu().float() - want).abs().max()), "max_err_causal": float((oc.cpu().float() - wantc).abs().max())}, f)
+
+
+def time_cfg3(f, rounds=5, shape=(4, 48, 8192, 64)):
+    B, H, N, D = shape
+    torch.manual_seed(1)
+    q, k, v = [torch.randn(B, H, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.empty_like(q)
+    fl = 4.0 * B * H * N * N * D
+    fns = {name: (lambda var=var: ops.fa2_fwd(q, k, v, o, variant=var)) for name, var in VARIANTS.items()}
+    fns["sdpa_cudnn"] = lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    res = {n: [] for n in fns}
+    for n in fns:
+        timeit(fns[n], 2)
+    for r in range(rounds):
+        for n in fns:
+            res[n].append(fl / timeit(fns[n], 5) * 1e-9)
+    for n, vals in res.items():
+        vs = sorted(vals)
+        emit({"what": "time", "shape": list(shape), "variant": n, "median": vs[len(vs) // 2], "min": vs[0], "max": vs[-1], "all": [round(x) for x in vals]}, f)
+    # causal: work is about half; report effective TFLOP/s on the causal flop count
+    flc = fl / 2
+    fnc = {"default_causal": lambda: ops.fa2_fwd(q, k, v, o, causal=True), "pf_causal": lambda: ops.fa2_fwd(q, k, v, o, causal=True, variant=0x40000),
+           "sdpa_causal": lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True)}
+    for n in fnc:
+        timeit(fnc[n], 2)
+    for n in fnc:
+        vals = [flc / timeit(fnc[n], 5) * 1e-9 for _ in range(3)]
+        emit({"what": "time_causal", "shape": list(shape), "variant": n, "median_tflops_on_half_flops": sorted(vals)[1]}, f)
+
+
+if __name__ == "__main__":
+    with open(os.path.join(OUT, "fa2_r2.jsonl"), "a") as f:
+        if sys.argv[1] == "check":
+            check(f)
+        else:
+            time_cfg3(f)

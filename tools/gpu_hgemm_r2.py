@@ -97,11 +97,13 @@ def time_all(f, sizes, rounds):
 
 
 def trace(f, n=8192):
+    if len(sys.argv) > 2:
+        n = int(sys.argv[2])
     a = torch.randn(n, n, dtype=torch.half, device="cuda")
     b = torch.randn(n, n, dtype=torch.half, device="cuda")
     c = torch.empty(n, n, dtype=torch.half, device="cuda")
     buf = torch.zeros(74 * 128, dtype=torch.int64, device="cuda")
-    for name, v in (("default", 0), ("sk_off", V2 | SK_OFF)):
+    for name, v in (("default", 0), ("t256_sk_off", V2 | SK_OFF), ("t256_sk_forced", V2 | (1 << 22))):
         for _ in range(3):
             ops.hgemm(a, b, c, variant=v)
         torch.cuda.synchronize()
@@ -116,6 +118,8 @@ def trace(f, n=8192):
         entry, setup, first, end = rel(t[:, 0]), rel(t[:, 1]), rel(t[:, 2]), rel(t[:, 3])
         mma = [[int(v - t0) for v in row.tolist() if v > 0] for row in t[:, 8:64]]
         epi = [[int(v - t0) for v in row.tolist() if v > 0] for row in t[:, 64:120]]
+        mma = [m if m else [0] for m in mma]
+        epi = [e if e else [0] for e in epi]
         emit({"what": "trace", "n": n, "cfg": name, "unit": "ns since first cluster's kernel entry",
               "entry_min_max": [min(entry), max(entry)], "setup_done_min_max": [min(setup), max(setup)],
               "first_stage_landed_min_max": [min(x for x in first if x is not None), max(x for x in first if x is not None)],
