@@ -436,6 +436,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="headline only (skip sweep / attention / ffpa / ref_gpu)")
+    ap.add_argument("--sections", default="all", help="comma list of the extra sections to run: sweep,attention,ffpa,widened,"
+                    "sharded (default all; the headline, e2e, roofline and cpu_baseline always run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -577,42 +579,44 @@ def main():
                             "hgemm_8192", 3.0 * n * n * 2, ms * args.steps)
     rooflines = {"hgemm_8192": roofline}
 
+    want = (lambda name: args.sections == "all" or name in args.sections.split(","))
     if not args.quick:
         # -------------------------------------------------------------- HGEMM sweep + cuBLAS (torch.matmul) + reference mma.sync
-        ref_h = load_ref_hgemm()
-        sweep = []
-        for m in SWEEP:
-            A = a[:m, :m].contiguous() if m <= n else torch.randn(m, m, dtype=torch.half, device=dev)
-            B = b[:m, :m].contiguous() if m <= n else torch.randn(m, m, dtype=torch.half, device=dev)
-            C = torch.empty(m, m, dtype=torch.half, device=dev)
-            it = 20 if m <= 8192 else 5
-            t_ours = cuda_time(lambda: ops.hgemm(A, B, C), it, 3)
-            launches += it + 3
-            t_cublas = cuda_time(lambda: torch.matmul(A, B, out=C), it, 3)
-            row = {"mnk": m, "tflops": 2.0 * m ** 3 / t_ours * 1e-9, "cublas_tflops": 2.0 * m ** 3 / t_cublas * 1e-9,
-                   "frac_of_peak_burst": 2.0 * m ** 3 / t_ours * 1e-9 / peaks["tflops_burst"],
-                   "frac_of_peak_sustained": 2.0 * m ** 3 / t_ours * 1e-9 / peaks["tflops_sustained"],
-                   "timed_region_ms": t_ours * it, "peak_regime": "burst" if t_ours * it < 100.0 else "sustained"}
-            if ref_h is not None:
-                best = None
-                for st in (2, 3, 4):
-                    stride = ref_swizzle_stride(m)
-                    stride = stride if stride in (512, 1024, 2048, 4096) and not (st == 4 and stride == 512) else 2048
-                    rc = ref_h.ref_hgemm_mma_stages_dsmem_nn(A.data_ptr(), B.data_ptr(), C.data_ptr(), m, m, m, st, stride)
-                    torch.cuda.synchronize()
-                    if rc != 0:
-                        continue
-                    t = cuda_time(lambda: ref_h.ref_hgemm_mma_stages_dsmem_nn(A.data_ptr(), B.data_ptr(), C.data_ptr(), m, m, m, st, stride),
-                                  5 if m > 8192 else 10, 2)
-                    tf = 2.0 * m ** 3 / t * 1e-9
-                    if best is None or tf > best[0]:
-                        best = (tf, st, stride)
-                if best:
-                    row["ref_mma_tflops"] = best[0]
-                    row["ref_mma_cfg"] = "hgemm_mma_m16n8k16_mma2x4_warp4x4x2_stages_dsmem stages=%d swizzle_stride=%d" % best[1:]
-            sweep.append(row)
-            del A, B, C
-        out["sweep"] = sweep
+        if want("sweep"):
+            ref_h = load_ref_hgemm()
+            sweep = []
+            for m in SWEEP:
+                A = a[:m, :m].contiguous() if m <= n else torch.randn(m, m, dtype=torch.half, device=dev)
+                B = b[:m, :m].contiguous() if m <= n else torch.randn(m, m, dtype=torch.half, device=dev)
+                C = torch.empty(m, m, dtype=torch.half, device=dev)
+                it = 20 if m <= 8192 else 5
+                t_ours = cuda_time(lambda: ops.hgemm(A, B, C), it, 3)
+                launches += it + 3
+                t_cublas = cuda_time(lambda: torch.matmul(A, B, out=C), it, 3)
+                row = {"mnk": m, "tflops": 2.0 * m ** 3 / t_ours * 1e-9, "cublas_tflops": 2.0 * m ** 3 / t_cublas * 1e-9,
+                       "frac_of_peak_burst": 2.0 * m ** 3 / t_ours * 1e-9 / peaks["tflops_burst"],
+                       "frac_of_peak_sustained": 2.0 * m ** 3 / t_ours * 1e-9 / peaks["tflops_sustained"],
+                       "timed_region_ms": t_ours * it, "peak_regime": "burst" if t_ours * it < 100.0 else "sustained"}
+                if ref_h is not None:
+                    best = None
+                    for st in (2, 3, 4):
+                        stride = ref_swizzle_stride(m)
+                        stride = stride if stride in (512, 1024, 2048, 4096) and not (st == 4 and stride == 512) else 2048
+                        rc = ref_h.ref_hgemm_mma_stages_dsmem_nn(A.data_ptr(), B.data_ptr(), C.data_ptr(), m, m, m, st, stride)
+                        torch.cuda.synchronize()
+                        if rc != 0:
+                            continue
+                        t = cuda_time(lambda: ref_h.ref_hgemm_mma_stages_dsmem_nn(A.data_ptr(), B.data_ptr(), C.data_ptr(), m, m, m, st, stride),
+                                      5 if m > 8192 else 10, 2)
+                        tf = 2.0 * m ** 3 / t * 1e-9
+                        if best is None or tf > best[0]:
+                            best = (tf, st, stride)
+                    if best:
+                        row["ref_mma_tflops"] = best[0]
+                        row["ref_mma_cfg"] = "hgemm_mma_m16n8k16_mma2x4_warp4x4x2_stages_dsmem stages=%d swizzle_stride=%d" % best[1:]
+                sweep.append(row)
+                del A, B, C
+            out["sweep"] = sweep
         del a, b, c
         torch.cuda.empty_cache()
 
@@ -645,79 +649,83 @@ def main():
                 r["sdpa_err"] = repr(e)[:160]
             return r
 
-        att["cfg3_fa2_b4_h48_n8192_d64"] = bench_attn(FA2_CFG3, ops.fa2_fwd, "fa2_cfg3_d64")
-        launches += 13
-        att["cfg5_shard_b4_h64_n8192_d128"] = bench_attn((4, 64, 8192, 128), ops.fa2_fwd, "fa2_cfg5_shard_d128")
-        launches += 13
-        out["attention"] = att
-        ffpa = bench_attn(FFPA_CFG4, ops.ffpa_fwd, "ffpa_cfg4_d512")
-        launches += 13
-        ref_ffpa = load_ref_module("pyffpa_cuda")
-        if ref_ffpa is not None:
-            try:
-                B_, H_, N_, D_ = FFPA_CFG4
-                q, k, v = [torch.randn(B_, H_, N_, D_, dtype=torch.half, device=dev) for _ in range(3)]
-                o2 = torch.zeros_like(q)
-                fl = 4.0 * B_ * H_ * N_ * N_ * D_
-                for name in ("ffpa_mma_acc_f32_L1", "ffpa_mma_acc_f16_L1"):
-                    best = 0.0
-                    for st in (1, 2, 3, 4):
-                        t2 = cuda_time(lambda: getattr(ref_ffpa, name)(q, k, v, o2, st), 3, 1)
-                        best = max(best, fl / t2 * 1e-9)
-                    ffpa["ref_" + name + "_tflops"] = best
-            except Exception as e:  # noqa
-                ffpa["ref_err"] = repr(e)[:160]
-        out["ffpa"] = {"cfg4_b1_h32_n4096_d512": ffpa}
-        torch.cuda.empty_cache()
-
-        # -------------------------------------------------------------- the widened rows (SURVEY 8f-3 / 8f-4), N = 1 only
-        if world == 1:
-            try:
-                gd = {}
-                for dt, nm in ((torch.bfloat16, "bf16"), (torch.float32, "tf32")):
-                    A = torch.randn(n, n, device=dev).to(dt)
-                    Bm = torch.randn(n, n, device=dev).to(dt)
-                    C = torch.empty(n, n, device=dev).to(dt)
-                    t_o = cuda_time(lambda: ops.gemm(A, Bm, C), 10, 3)
-                    launches += 13
-                    prev = torch.backends.cuda.matmul.allow_tf32
-                    torch.backends.cuda.matmul.allow_tf32 = True
-                    t_c = cuda_time(lambda: torch.matmul(A, Bm, out=C), 10, 3)
-                    torch.backends.cuda.matmul.allow_tf32 = prev
-                    gd[nm + "_8192"] = {"tflops": flops / t_o * 1e-9, "cublas_tflops": flops / t_c * 1e-9}
-                    del A, Bm, C
-                out["gemm_dtypes"] = gd
-            except Exception as e:  # noqa
-                out["gemm_dtypes"] = {"error": repr(e)[:200]}
-            try:
-                hbm = peaks.get("hbm_gbs")
-                ne = 64 * 1024 * 1024
-                xa, xb = torch.randn(ne, device=dev), torch.randn(ne, device=dev)
-                xc = torch.empty_like(xa)
-                xr = torch.randn(16384, 8192, dtype=torch.half, device=dev)
-                yr = torch.empty_like(xr)
-                sup = {}
-                for nm, fn, nbytes in (
-                        ("elementwise_add_f32", lambda: ops.elementwise_add(xa, xb, xc), 3 * ne * 4),
-                        ("block_all_reduce_sum_f32", lambda: ops.block_all_reduce_sum(xa), ne * 4),
-                        ("safe_softmax_f16_h8192", lambda: ops.softmax(xr, yr, ops.SOFTMAX_SAFE), 2 * xr.numel() * 2),
-                        ("rms_norm_f16_k8192", lambda: ops.rms_norm(xr, yr, 1.0), 2 * xr.numel() * 2),
-                        ("layer_norm_f16_k8192", lambda: ops.layer_norm(xr, yr, 1.0, 0.0), 2 * xr.numel() * 2),
-                        ("gelu_f32", lambda: ops.activation(xa, xc, "gelu"), 2 * ne * 4),
-                        ("dot_prod_f32", lambda: ops.dot_prod(xa, xb), 2 * ne * 4)):
-                    t_s = cuda_time(fn, 10, 3)
-                    launches += 13
-                    sup[nm] = {"gbps": nbytes / t_s * 1e-6, "frac_of_measured_hbm_peak": (nbytes / t_s * 1e-6 / hbm) if hbm else None}
-                out["support_hbm"] = sup
-                del xa, xb, xc, xr, yr
-            except Exception as e:  # noqa
-                out["support_hbm"] = {"error": repr(e)[:200]}
+        if want("attention"):
+            att["cfg3_fa2_b4_h48_n8192_d64"] = bench_attn(FA2_CFG3, ops.fa2_fwd, "fa2_cfg3_d64")
+            launches += 13
+            att["cfg5_shard_b4_h64_n8192_d128"] = bench_attn((4, 64, 8192, 128), ops.fa2_fwd, "fa2_cfg5_shard_d128")
+            launches += 13
+            out["attention"] = att
+        if want("ffpa"):
+            ffpa = bench_attn(FFPA_CFG4, ops.ffpa_fwd, "ffpa_cfg4_d512")
+            launches += 13
+            ref_ffpa = load_ref_module("pyffpa_cuda")
+            if ref_ffpa is not None:
+                try:
+                    B_, H_, N_, D_ = FFPA_CFG4
+                    q, k, v = [torch.randn(B_, H_, N_, D_, dtype=torch.half, device=dev) for _ in range(3)]
+                    o2 = torch.zeros_like(q)
+                    fl = 4.0 * B_ * H_ * N_ * N_ * D_
+                    for name in ("ffpa_mma_acc_f32_L1", "ffpa_mma_acc_f16_L1"):
+                        best = 0.0
+                        for st in (1, 2, 3, 4):
+                            t2 = cuda_time(lambda: getattr(ref_ffpa, name)(q, k, v, o2, st), 3, 1)
+                            best = max(best, fl / t2 * 1e-9)
+                        ffpa["ref_" + name + "_tflops"] = best
+                except Exception as e:  # noqa
+                    ffpa["ref_err"] = repr(e)[:160]
+            out["ffpa"] = {"cfg4_b1_h32_n4096_d512": ffpa}
             torch.cuda.empty_cache()
 
+        # -------------------------------------------------------------- the widened rows (SURVEY 8f-3 / 8f-4), N = 1 only
+        if want("widened"):
+            if world == 1:
+                try:
+                    gd = {}
+                    for dt, nm in ((torch.bfloat16, "bf16"), (torch.float32, "tf32")):
+                        A = torch.randn(n, n, device=dev).to(dt)
+                        Bm = torch.randn(n, n, device=dev).to(dt)
+                        C = torch.empty(n, n, device=dev).to(dt)
+                        t_o = cuda_time(lambda: ops.gemm(A, Bm, C), 10, 3)
+                        launches += 13
+                        prev = torch.backends.cuda.matmul.allow_tf32
+                        torch.backends.cuda.matmul.allow_tf32 = True
+                        t_c = cuda_time(lambda: torch.matmul(A, Bm, out=C), 10, 3)
+                        torch.backends.cuda.matmul.allow_tf32 = prev
+                        gd[nm + "_8192"] = {"tflops": flops / t_o * 1e-9, "cublas_tflops": flops / t_c * 1e-9}
+                        del A, Bm, C
+                    out["gemm_dtypes"] = gd
+                except Exception as e:  # noqa
+                    out["gemm_dtypes"] = {"error": repr(e)[:200]}
+                try:
+                    hbm = peaks.get("hbm_gbs")
+                    ne = 64 * 1024 * 1024
+                    xa, xb = torch.randn(ne, device=dev), torch.randn(ne, device=dev)
+                    xc = torch.empty_like(xa)
+                    xr = torch.randn(16384, 8192, dtype=torch.half, device=dev)
+                    yr = torch.empty_like(xr)
+                    sup = {}
+                    for nm, fn, nbytes in (
+                            ("elementwise_add_f32", lambda: ops.elementwise_add(xa, xb, xc), 3 * ne * 4),
+                            ("block_all_reduce_sum_f32", lambda: ops.block_all_reduce_sum(xa), ne * 4),
+                            ("safe_softmax_f16_h8192", lambda: ops.softmax(xr, yr, ops.SOFTMAX_SAFE), 2 * xr.numel() * 2),
+                            ("rms_norm_f16_k8192", lambda: ops.rms_norm(xr, yr, 1.0), 2 * xr.numel() * 2),
+                            ("layer_norm_f16_k8192", lambda: ops.layer_norm(xr, yr, 1.0, 0.0), 2 * xr.numel() * 2),
+                            ("gelu_f32", lambda: ops.activation(xa, xc, "gelu"), 2 * ne * 4),
+                            ("dot_prod_f32", lambda: ops.dot_prod(xa, xb), 2 * ne * 4)):
+                        t_s = cuda_time(fn, 10, 3)
+                        launches += 13
+                        sup[nm] = {"gbps": nbytes / t_s * 1e-6, "frac_of_measured_hbm_peak": (nbytes / t_s * 1e-6 / hbm) if hbm else None}
+                    out["support_hbm"] = sup
+                    del xa, xb, xc, xr, yr
+                except Exception as e:  # noqa
+                    out["support_hbm"] = {"error": repr(e)[:200]}
+                torch.cuda.empty_cache()
+
         # -------------------------------------------------------------- config #5: batch-sharded attention over the ranks
-        sharded_rec = bench_sharded_cfg5(world, rank, dev, barrier, dist_on, peaks)
-        launches += sharded_rec.pop("_launches", 0)
-        e2e["sharded_attention"] = sharded_rec
+        if want("sharded"):
+            sharded_rec = bench_sharded_cfg5(world, rank, dev, barrier, dist_on, peaks)
+            launches += sharded_rec.pop("_launches", 0)
+            e2e["sharded_attention"] = sharded_rec
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu_baseline = None

@@ -34,3 +34,27 @@ gv = torch.randn(1000, 1, device="cuda"); gy = torch.empty(77, 1, device="cuda")
 ops.rope_f32(x, y, True); ops.rope_f32(x, y, False)
 torch.cuda.synchronize()
 print("sanitize run done")
+# round-2 additions: 512x256 pair tile, stream-K remainder round (forced on a small problem), A^T storage, the masked and
+# bf16 attention builds, CTA-pair FFPA at D = 768 / 1024
+a2 = torch.randn(1024, 520, dtype=torch.half, device="cuda"); b2 = torch.randn(520, 768, dtype=torch.half, device="cuda")
+c2 = torch.empty(1024, 768, dtype=torch.half, device="cuda")
+ops.hgemm(a2, b2, c2, variant=4)
+ops.hgemm(a2, b2, c2, variant=2 | (1 << 22))      # stream-K forced (12 tiles, 74 clusters)
+a3 = torch.randn(5120, 512, dtype=torch.half, device="cuda"); b3 = torch.randn(512, 4096, dtype=torch.half, device="cuda")
+c3 = torch.empty(5120, 4096, dtype=torch.half, device="cuda")
+ops.hgemm(a3, b3, c3, variant=2)                   # 320 tiles: 24 of them stream-K
+ops.gemm(a2.t().contiguous().t(), b2, c2, a_km=True)
+for D in (64, 128):
+    q, k, v = [torch.randn(2, 2, 333, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.empty_like(q)
+    sl = torch.tensor([333, 100], dtype=torch.int32, device="cuda")
+    ops.fa2_fwd(q, k, v, o, causal=True, seqlens_k=sl)
+    qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    ob = torch.empty_like(qb)
+    ops.fa2_fwd(qb, kb, vb, ob, causal=True)
+for D in (768, 1024):
+    q, k, v = [torch.randn(1, 1, 300, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.empty_like(q)
+    ops.ffpa_fwd(q, k, v, o)
+torch.cuda.synchronize()
+print("sanitize run (round 2 additions) done")
