@@ -286,31 +286,70 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (w.kind < 0) break;
         const int acc = it % Cfg::NACC;
         const uint32_t acc_phase = (it / Cfg::NACC) & 1;
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::MT * BN;
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+        // one k-block: the MMAs of accumulator blocks [mt0, mt1) on the operand stage `st`
+        auto issue_kblock = [&](int st, int kb, int mt0, int mt1) {
+          const uint32_t sa = smem_tiles + st * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; ++k) {
+            const uint64_t bdesc = smem_desc(b_hi, sb + k * b_kstep);
+#pragma unroll
+            for (int mt = 0; mt < Cfg::MT; ++mt) {   // rows [mt*128, mt*128+128) of this CTA's A stage, same B
+              if (mt < mt0 || mt >= mt1) continue;
+              const uint64_t adesc = smem_desc(a_hi, sa + mt * (128 * 128) + k * a_kstep);
+              umma_ss<CG, (Cfg::DT == 2)>(d_tmem + mt * BN, adesc, bdesc, idesc, (kb > w.kb0 || k != 0) ? 1u : 0u);
+            }
+          }
+        };
+        auto commit_kblock = [&](int st, int kb) {
+          if constexpr (CG == 2) umma_commit_2sm(bar_empty + 8 * st, 0b11);
+          else umma_commit(bar_empty + 8 * st);
+          if (kb == w.kb1 - 1) {  // accumulator complete: publish it to the epilogue warps
+            if constexpr (CG == 2) umma_commit_2sm(bar_tfull + 8 * acc, 0b11);
+            else umma_commit(bar_tfull + 8 * acc);
+          }
+        };
+        int kb = w.kb0;
+        if constexpr (Cfg::MT == 2) {
+          // Both accumulators of a tile fill TMEM, so the epilogue of tile i cannot hide behind tile i+1 as a whole.  But
+          // the epilogue drains block 0 first and hands it back on its own barrier: the first PRE k-blocks of the next
+          // tile (the operand stages the producer has already filled) are issued for block 0 alone while block 1 is
+          // still being read out, then for block 1, releasing the stages; the rest of the tile runs both blocks per stage.
+          const int pre = min(STAGES, w.kb1 - w.kb0);
+          mbar_wait(bar_tempty + 0, acc_phase ^ 1);
+          tc_fence_after();
+          int st = stage;
+          uint32_t ph = phase;
+          for (int p = 0; p < pre; ++p) {
+            mbar_wait(bar_full + 8 * st, ph);
+            tc_fence_after();
+            if (trace && it == 0 && p == 0 && lane == 0) trace[2] = global_timer();
+            if (elect_one()) issue_kblock(st, kb + p, 0, 1);
+            __syncwarp();
+            if (++st == STAGES) { st = 0; ph ^= 1; }
+          }
+          mbar_wait(bar_tempty + 8, acc_phase ^ 1);
+          tc_fence_after();
+          for (int p = 0; p < pre; ++p, ++kb) {
+            if (elect_one()) {
+              issue_kblock(stage, kb, 1, 2);
+              commit_kblock(stage, kb);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+          tc_fence_after();
+        }
+        for (; kb < w.kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           if (trace && it == 0 && kb == w.kb0 && lane == 0) trace[2] = global_timer();
-          const uint32_t sa = smem_tiles + stage * Cfg::STAGE_BYTES;
-          const uint32_t sb = sa + Cfg::A_BYTES;
           if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; ++k) {
-              const uint64_t bdesc = smem_desc(b_hi, sb + k * b_kstep);
-#pragma unroll
-              for (int mt = 0; mt < Cfg::MT; ++mt) {   // rows [mt*128, mt*128+128) of this CTA's A stage, same B
-                const uint64_t adesc = smem_desc(a_hi, sa + mt * (128 * 128) + k * a_kstep);
-                umma_ss<CG, (Cfg::DT == 2)>(d_tmem + mt * BN, adesc, bdesc, idesc, (kb > w.kb0 || k != 0) ? 1u : 0u);
-              }
-            }
-            if constexpr (CG == 2) umma_commit_2sm(bar_empty + 8 * stage, 0b11);
-            else umma_commit(bar_empty + 8 * stage);
-            if (kb == w.kb1 - 1) {  // accumulator complete: publish it to the epilogue warps
-              if constexpr (CG == 2) umma_commit_2sm(bar_tfull + 8 * acc, 0b11);
-              else umma_commit(bar_tfull + 8 * acc);
-            }
+            issue_kblock(stage, kb, 0, Cfg::MT);
+            commit_kblock(stage, kb);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -410,13 +449,13 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tma_store_commit();
         }
       };
-      auto release_tmem = [&]() {
-        // accumulator fully read: hand the TMEM buffer back to the MMA warp
+      auto release_tmem = [&](int which) {
+        // accumulator (MT = 2: accumulator block `which`) fully read: hand the TMEM columns back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_cluster(mapa(bar_tempty + 8 * acc, 0));
-          else mbar_arrive(bar_tempty + 8 * acc);
+          if constexpr (CG == 2) mbar_arrive_cluster(mapa(bar_tempty + 8 * which, 0));
+          else mbar_arrive(bar_tempty + 8 * which);
         }
       };
       static_assert(NCHUNK % 2 == 0, "chunk pairs");
@@ -428,8 +467,9 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         load_chunk(c + 1, rb);
         process_chunk(c, ra);
         tmem_wait_ld();            // chunk c+1 is in rb
+        if (Cfg::MT == 2 && c + 2 == NCHUNK / 2) release_tmem(0);   // block 0 is out: the next tile may start on it
         if (c + 2 < NCHUNK) load_chunk(c + 2, ra);
-        else release_tmem();
+        else release_tmem(Cfg::MT == 2 ? 1 : acc);
         process_chunk(c + 1, rb);
       }
       if (w.kind == 1) {
