@@ -229,6 +229,15 @@ def roofline_obj(kernel, flops, ms, peaks, traffic_key, algo_bytes, timed_region
             "algorithmic_bytes_per_launch": algo_bytes, "traffic": traffic, "traffic_source": src}
 
 
+def headline_config():
+    """`config` of the JSON line - identical for both arms (the driver compares them)."""
+    return {"workload": "hgemm_nn_f16_m8192_n8192_k8192", "baseline_config": "#2 HGEMM fp16 NN square",
+            "multi_gpu": "replicas only (a single GEMM does not shard without a collective)",
+            "l2": "operands 3 x 128 MiB > 126 MB L2 (inputs larger than L2, no flush needed)",
+            "preconditioning": "40 untimed launches + 1 s pause before the W warm-up steps (GPU out of its idle P-state)",
+            "randn_seed": 1}
+
+
 def run_reference_impl(args, world, rank):
     """--impl reference: the reference's CPU-runnable path (torch.matmul on host cores), rank 0 only."""
     if rank != 0:
@@ -248,8 +257,9 @@ def run_reference_impl(args, world, rank):
     line = {"impl": "reference", "metric": "hgemm_tflops", "value": v, "unit": "TFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (cpu)", "data": "synthetic",
-            "config": {"workload": "hgemm_nn_f16_m8192_n8192_k8192", "note": "reference arm = torch.matmul on host cores "
-                       "(the reference's own CPU-runnable comparator); ms_per_step extrapolated from the sample"},
+            "config": headline_config(),
+            "reference_note": "reference arm = torch.matmul on host cores (the reference's own CPU-runnable comparator, "
+                              "kernels/hgemm/hgemm.py:L349); each step is a bounded row-slab sample, ms_per_step extrapolated",
             "cpu_baseline": {"value": v, "unit": "TFLOP/s", "cores": info["cores"], "kind": "port", "sample": sample,
                              "cpu": info["model"]},
             "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -741,11 +751,7 @@ def main():
         line = {"metric": "hgemm_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
-                "config": {"workload": "hgemm_nn_f16_m8192_n8192_k8192", "baseline_config": "#2 HGEMM fp16 NN square",
-                           "multi_gpu": "replicas only (a single GEMM does not shard without a collective)",
-                           "l2": "operands 3 x 128 MiB > 126 MB L2 (inputs larger than L2, no flush needed)",
-                           "preconditioning": "40 untimed launches + 1 s pause before the W warm-up steps (GPU out of its idle P-state)",
-                           "randn_seed": 1},
+                "config": headline_config(),
                 "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline,
                 "config1_sgemm_cpu": config1,
                 "clocks": clocks, "peaks": peaks,

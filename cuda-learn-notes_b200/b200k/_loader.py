@@ -71,6 +71,7 @@ _SIGS = {
     "b200k_max_i32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "b200k_histogram_i32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "b200k_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "b200k_transpose_u16_batched": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "b200k_debug_set_trace": (c_int, [c_void_p]),
     "b200k_debug_set_hgemm_trace": (c_int, [c_void_p]),
     "b200k_activation": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),

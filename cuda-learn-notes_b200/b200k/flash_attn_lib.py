@@ -46,7 +46,10 @@ def _make(short: str, max_d: int):
             _ops.fa2_fwd(Q, K, V, O, v_is_dn=v_is_dn)
         else:
             if v_is_dn:
-                V = V.transpose(-2, -1).contiguous()
+                # the large-head-dim kernel consumes V as [B,H,N,D]: transpose with the library's own kernel
+                Vt = torch.empty(Q.shape, dtype=V.dtype, device=V.device)
+                _ops.transpose_16bit_batched(V, Vt)
+                V = Vt
             _ops.ffpa_fwd(Q, K, V, O)
 
     fn.__name__ = fn.__qualname__ = name

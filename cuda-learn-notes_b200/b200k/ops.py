@@ -365,6 +365,19 @@ def mat_transpose(x, y) -> None:
         L.check(_lib.b200k_mat_transpose_f32(x.data_ptr(), y.data_ptr(), x.size(0), x.size(1), _stream(x)))
 
 
+def transpose_16bit_batched(x: torch.Tensor, y: torch.Tensor) -> None:
+    """y[..., N, M] = x[..., M, N]^T for f16 / bf16 tensors (leading dims are the batch); exact."""
+    if x.dtype not in (torch.float16, torch.bfloat16):
+        raise RuntimeError("values must be torch::kHalf or torch::kBFloat16")
+    _check_dtype(y, x.dtype)
+    if x.dim() < 2 or y.numel() != x.numel():
+        raise RuntimeError("Tensor size mismatch!")
+    _check_cuda_contig(x, y)
+    M, N = x.size(-2), x.size(-1)
+    with _DeviceGuard(x):
+        L.check(_lib.b200k_transpose_u16_batched(x.data_ptr(), y.data_ptr(), x.numel() // (M * N), M, N, _stream(x)))
+
+
 def gemv(a, x, y) -> None:
     """y[M,1] = a[M,K] @ x[K,1], f32 or f16 with f32 accumulation (kernels/sgemv/sgemv.cu:L126-195, hgemv.cu:L130-199)."""
     if a.dtype not in (torch.float32, torch.float16):

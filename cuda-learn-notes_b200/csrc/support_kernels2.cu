@@ -387,6 +387,35 @@ __global__ void __launch_bounds__(kThreads) transpose_f32_kernel(const float* __
   }
 }
 
+// Batched transpose of 16-bit elements: y[b][N,M] = x[b][M,N]^T.  Used by the drop-in `*_swizzle_qkv` attention entry points
+// for head dims above 128, which receive V as [B,H,D,N] while the FFPA kernel consumes [B,H,N,D].  64 x 64 tiles through
+// shared memory (row padded by one 32-bit word), 4-byte global accesses both ways (2 elements), exact.
+__global__ void __launch_bounds__(kThreads) transpose_u16_batched_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
+                                                                         int M, int N, int tiles_m, int tiles_n, int64_t tiles) {
+  __shared__ uint16_t tile[kTile][kTile + 2];
+  const int64_t per_batch = int64_t(tiles_m) * tiles_n;
+  for (int64_t tidx = blockIdx.x; tidx < tiles; tidx += gridDim.x) {
+    const int64_t b = tidx / per_batch;
+    const int t = int(tidx - b * per_batch);
+    const int m0 = (t / tiles_n) * kTile, n0 = (t % tiles_n) * kTile;
+    const uint16_t* xb = x + b * int64_t(M) * N;
+    uint16_t* yb = y + b * int64_t(M) * N;
+    const int tx = threadIdx.x % kTile, ty = threadIdx.x / kTile;  // 64 x 4
+#pragma unroll 4
+    for (int r = ty; r < kTile; r += kThreads / kTile) {
+      const int m = m0 + r, nn = n0 + tx;
+      if (m < M && nn < N) tile[r][tx] = xb[int64_t(m) * N + nn];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = ty; r < kTile; r += kThreads / kTile) {
+      const int nn = n0 + r, m = m0 + tx;
+      if (nn < N && m < M) yb[int64_t(nn) * M + m] = tile[tx][r];
+    }
+    __syncthreads();
+  }
+}
+
 // ============================================================================================ GEMV
 // y[m] = sum_k A[m,k] x[k]: one warp per row, 16-byte loads of the row (streamed) and of x (re-read by every warp, L1 /
 // L2 resident), fp32 accumulation, shuffle reduction.  HBM-bound on A.  The reference's k32 / k128 / k16 entry points
@@ -509,6 +538,22 @@ extern "C" int b200k_mat_transpose_f32(const void* x, void* y, int64_t M, int64_
     transpose_f32_kernel<true><<<grid, kThreads, 0, s>>>(xp, yp, int(M), int(N), tiles_n, tiles);
   else
     transpose_f32_kernel<false><<<grid, kThreads, 0, s>>>(xp, yp, int(M), int(N), tiles_n, tiles);
+  B200K_CHECK_CUDA(cudaGetLastError());
+  return B200K_OK;
+}
+
+extern "C" int b200k_transpose_u16_batched(const void* x, void* y, int64_t batch, int64_t M, int64_t N, void* stream) {
+  if (!x || !y) return set_error(B200K_EARG, "b200k_transpose_u16_batched: null pointer");
+  if (batch < 1 || M < 1 || N < 1 || M > INT32_MAX || N > INT32_MAX)
+    return set_error(B200K_ESHAPE, "b200k_transpose_u16_batched: need batch >= 1, 1 <= M, N < 2^31");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const int tiles_m = int((M + kTile - 1) / kTile), tiles_n = int((N + kTile - 1) / kTile);
+  const int64_t tiles = batch * tiles_m * tiles_n;
+  const int grid = grid_for(tiles, 1, di.sm_count, 16);
+  transpose_u16_batched_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), int(M), int(N), tiles_m, tiles_n, tiles);
   B200K_CHECK_CUDA(cudaGetLastError());
   return B200K_OK;
 }

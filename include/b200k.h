@@ -187,6 +187,9 @@ int b200k_mat_transpose_f32(const void* x, void* y, int64_t M, int64_t N, void* 
 /* y[M] = A[M,K] x[K], dtype F32 or F16 (f32 accumulation; the reference's hgemv accumulates in half).
  * kernels/sgemv/sgemv.cu:L20-104 (sgemv_k32_f32, sgemv_k128_f32x4, sgemv_k16_f32), kernels/hgemv/hgemv.cu:L24-108. */
 int b200k_gemv(const void* a, const void* x, void* y, int64_t M, int64_t K, int dtype, void* stream);
+/* y[b][N,M] = x[b][M,N]^T for 16-bit elements (f16 / bf16), `batch` matrices back to back; exact.  Used by the drop-in
+ * flash_attn_mma_stages_*_swizzle_qkv entry points for head dims above 128 (V arrives as [B,H,D,N], flash_attn.cc:L128-159). */
+int b200k_transpose_u16_batched(const void* x, void* y, int64_t batch, int64_t M, int64_t N, void* stream);
 
 /* Debug hook, not part of the drop-in surface: device buffer of 3*32*8 uint64 that the next traced FA-2 launch
  * (variant | 0x100, D = 64 or 128) fills with clock64() stamps of CTA (0,0); see tools/gpu_trace_fa2.py. */

@@ -159,3 +159,28 @@ def test_shim_namespaces_route_to_the_kernels():
     with pytest.raises(RuntimeError, match="K must be multiple of 128"):
         S.sgemv_lib.sgemv_k128_f32x4(torch.randn(4, 32, device="cuda"), torch.randn(32, 1, device="cuda"),
                                      torch.empty(4, 1, device="cuda"))
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 256, 1000), (1, 1, 64, 64), (1, 2, 77, 130), (4, 8, 256, 8192)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_transpose_16bit_batched_bit_exact(shape, dtype):
+    from b200k import ops
+
+    torch.manual_seed(sum(shape))
+    x = torch.randn(*shape, device="cuda").to(dtype)
+    y = torch.empty(*shape[:-2], shape[-1], shape[-2], dtype=dtype, device="cuda")
+    ops.transpose_16bit_batched(x, y)
+    assert torch.equal(y, x.transpose(-2, -1).contiguous())
+
+
+def test_transposed_v_entry_point_large_headdim():
+    """flash_attn_mma_stages_split_q_tiling_qk_swizzle_qkv with D = 256: V arrives as [B,H,D,N] (flash_attn.cc:L128-159)."""
+    from b200k import flash_attn_lib
+    from oracle import oracle
+
+    torch.manual_seed(3)
+    B, H, N, D = 1, 2, 512, 256
+    q, k, v = [torch.randn(B, H, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.zeros_like(q)
+    flash_attn_lib.flash_attn_mma_stages_split_q_tiling_qk_swizzle_qkv(q, k, v.transpose(-2, -1).contiguous(), o, 1)
+    assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), rtol=1e-2, atol=1e-3)

@@ -73,7 +73,9 @@ def test_fa2_vs_reference_share_qkv(shape):
     ops.fa2_fwd(q, k, v, o)
     want = oracle.attention(q, k, v).float()
     assert torch.allclose(o.float(), o_ref32.float(), rtol=1e-2, atol=1e-3)
-    assert torch.allclose(o.float(), o_ref16.float(), rtol=1e-2, atol=2e-3)
+    # the f16-accumulating twin: atol 1e-3 + twice its own deviation from the fp32 oracle (it accumulates QK^T and PV in half)
+    err16 = float((o_ref16.cpu().float() - want).abs().max())
+    assert torch.allclose(o.float(), o_ref16.float(), rtol=1e-2, atol=1e-3 + 2.0 * err16), err16
     # and the oracle sits where both do
     assert torch.allclose(o_ref32.cpu().float(), want, rtol=1e-2, atol=1e-3)
     assert (o.cpu().float() - want).abs().max() <= (o_ref16.cpu().float() - want).abs().max() + 1e-4
@@ -92,3 +94,91 @@ def test_ffpa_vs_reference(shape):
     o = torch.zeros_like(q)
     ops.ffpa_fwd(q, k, v, o)
     assert torch.allclose(o.float(), o_ref.float(), rtol=1e-2, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE-size cases
+def _fp32_heads(q, k, v, heads):
+    """fp32 attention on the GPU for a few (b, h) pairs: the exact-arithmetic yardstick at sizes the CPU oracle cannot hold."""
+    out = {}
+    for b, h in heads:
+        s = (q[b, h].float() @ k[b, h].float().t()) / q.size(-1) ** 0.5
+        out[(b, h)] = torch.softmax(s, -1) @ v[b, h].float()
+    return out
+
+
+@pytest.mark.parametrize("shape,tag", [((4, 48, 8192, 64), "config #3"), ((4, 64, 8192, 128), "config #5 shard")])
+def test_fa2_vs_reference_at_baseline_size(shape, tag):
+    """The whole output tensor of BASELINE configs #3 and #5 (one GPU's shard) against the reference's own
+    flash_attn_mma_stages_split_q_shared_qkv kernels on identical inputs, north-star tolerance rtol 1e-2 / atol 1e-3.
+    The f16-accumulating twin is compared with atol = 1e-3 + its OWN measured error against fp32 arithmetic: it
+    accumulates QK^T and PV in half, and at N = 8192 that error alone can exceed 1e-3 - the product (fp32 accumulation)
+    must not be asked to reproduce it."""
+    from b200k import ops
+
+    ref = _ref_module("ref_flash_attn_lib")
+    B, H, N, D = shape
+    torch.manual_seed(1)
+    q, k, v = [torch.randn(B, H, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.zeros_like(q)
+    ops.fa2_fwd(q, k, v, o)
+    o32 = torch.zeros_like(q)
+    ref.flash_attn_mma_stages_split_q_shared_qkv_acc_f32(q, k, v, o32, 2)
+    assert torch.allclose(o.float(), o32.float(), rtol=1e-2, atol=1e-3), tag
+    heads = [(0, 0), (B - 1, H - 1)]
+    exact = _fp32_heads(q, k, v, heads)
+    o16 = torch.zeros_like(q)
+    ref.flash_attn_mma_stages_split_q_shared_qkv(q, k, v, o16, 2)
+    err16 = max(float((o16[b, h].float() - exact[(b, h)]).abs().max()) for b, h in heads)
+    err_ours = max(float((o[b, h].float() - exact[(b, h)]).abs().max()) for b, h in heads)
+    assert err_ours <= 1e-3 and err_ours <= err16 + 1e-4, (tag, err_ours, err16)
+    assert torch.allclose(o.float(), o16.float(), rtol=1e-2, atol=1e-3 + 2.0 * err16), (tag, err16)
+
+
+def test_ffpa_vs_reference_at_config4():
+    """BASELINE config #4 (1,32,4096,512): whole tensor against both reference twins (ffpa_mma_acc_f32_L1 / _f16_L1)."""
+    from b200k import ops
+
+    ref = _ref_module("pyffpa_cuda")
+    B, H, N, D = 1, 32, 4096, 512
+    torch.manual_seed(4)
+    q, k, v = [torch.randn(B, H, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.zeros_like(q)
+    ops.ffpa_fwd(q, k, v, o)
+    o32, o16 = torch.zeros_like(q), torch.zeros_like(q)
+    ref.ffpa_mma_acc_f32_L1(q, k, v, o32, 2)
+    ref.ffpa_mma_acc_f16_L1(q, k, v, o16, 2)
+    assert torch.allclose(o.float(), o32.float(), rtol=1e-2, atol=1e-3)
+    heads = [(0, 0), (0, H - 1)]
+    exact = _fp32_heads(q, k, v, heads)
+    err16 = max(float((o16[b, h].float() - exact[(b, h)]).abs().max()) for b, h in heads)
+    err_ours = max(float((o[b, h].float() - exact[(b, h)]).abs().max()) for b, h in heads)
+    assert err_ours <= 1e-3 and err_ours <= err16 + 1e-4, (err_ours, err16)
+    assert torch.allclose(o.float(), o16.float(), rtol=1e-2, atol=1e-3 + 2.0 * err16), err16
+
+
+@pytest.mark.parametrize("n", [4096, 8192])
+def test_hgemm_vs_reference_mma_kernel_at_sweep_sizes(n):
+    """BASELINE config #2 sizes against the reference's flagship mma.sync kernel (fp16 accumulate): ours at least as
+    close to exact arithmetic, and inside the reference's own error of it."""
+    from b200k import ops
+
+    p = os.path.join(REF_DIR, "libref_hgemm.so")
+    if not os.path.exists(p):
+        pytest.skip("libref_hgemm.so not built")
+    lib = ctypes.CDLL(p)
+    lib.ref_hgemm_mma_stages_dsmem_nn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 5
+    torch.manual_seed(n)
+    a = torch.randn(n, n, dtype=torch.half, device="cuda")
+    b = torch.randn(n, n, dtype=torch.half, device="cuda")
+    c_ref = torch.zeros(n, n, dtype=torch.half, device="cuda")
+    c = torch.zeros(n, n, dtype=torch.half, device="cuda")
+    assert lib.ref_hgemm_mma_stages_dsmem_nn(a.data_ptr(), b.data_ptr(), c_ref.data_ptr(), n, n, n, 2, 2048) == 0
+    torch.cuda.synchronize()
+    ops.hgemm(a, b, c)
+    rows = torch.arange(0, n, n // 64, device="cuda")
+    exact = a[rows].double() @ b.double()
+    e_ours = (c[rows].double() - exact).abs()
+    e_ref = (c_ref[rows].double() - exact).abs()
+    assert e_ours.max() <= e_ref.max() and e_ours.pow(2).mean() <= e_ref.pow(2).mean()
+    assert e_ours.max() <= exact.abs().max() * 2.0 ** -10
+    assert (c.float() - c_ref.float()).abs().max() <= e_ref.max() * 4 + 1e-2      # whole tensor, bounded by the reference's own error
