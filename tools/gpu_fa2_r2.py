@@ -10,8 +10,7 @@ from oracle import oracle
 
 OUT = os.path.join(ROOT, "gpurun_out", "r2")
 os.makedirs(OUT, exist_ok=True)
-VARIANTS = {"default": 0, "pf_bc64": 0x40000, "bc64": 0x80000, "pf_bc64_nopoly": 0x40000 | (7 << 14), "default_nopoly": 7 << 14,
-            "pf_bc64_np1": 0x40000 | (1 << 12)}
+VARIANTS = {"default": 0, "split_s": 0x40000, "split_s_nopoly": 0x40000 | (7 << 14), "default_nopoly": 7 << 14}
 
 
 def emit(rec, f):
@@ -31,7 +30,7 @@ def timeit(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-def check(f, D=64):
+def check(f, D=128):
     for shape in [(1, 2, 256, D), (1, 1, 64, D), (1, 1, 65, D), (2, 3, 1000, D), (1, 1, 1, D), (1, 2, 128, D), (1, 2, 192, D),
                   (1, 1, 333, D), (1, 4, 2048, D)]:
         torch.manual_seed(shape[2])
@@ -49,7 +48,7 @@ def check(f, D=64):
                   "max_err": float((o.cpu().float() - want).abs().max()), "max_err_causal": float((oc.cpu().float() - wantc).abs().max())}, f)
 
 
-def time_cfg3(f, rounds=5, shape=(4, 48, 8192, 64)):
+def time_cfg3(f, rounds=5, shape=(4, 64, 8192, 128)):
     B, H, N, D = shape
     torch.manual_seed(1)
     q, k, v = [torch.randn(B, H, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
