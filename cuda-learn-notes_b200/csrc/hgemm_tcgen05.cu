@@ -608,6 +608,9 @@ static int gemm_dispatch(const char* who, const void* A, const void* B, void* C,
   if ((K % PACK) || (N % PACK))
     return set_error(B200K_ESHAPE, "%s: K and N must be multiples of %d (16-byte rows), got K=%lld N=%lld", who, PACK,
                      (long long)K, (long long)N);
+  if (a_is_km && DT == 2) return set_error(B200K_EDTYPE, "%s: A stored as [K,M] is built for f16 / bf16 only", who);
+  if (a_is_km && (M % PACK))
+    return set_error(B200K_ESHAPE, "%s: M must be a multiple of %d when A is stored as [K,M]", who, PACK);
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;

@@ -47,6 +47,14 @@ def test_argument_validation_happens_before_cuda():
     assert lib.b200k_mat_transpose_f32(one, None, 4, 4, None) == L.EARG
     assert lib.b200k_gemv(one, one, one, 4, 0, L.F32, None) == L.ESHAPE
     assert lib.b200k_dot_prod(one, one, None, 4, L.F32, one, None) == L.EARG
+    # round-2 entry points
+    assert lib.b200k_fa2_fwd(one, one, one, one, 1, 1, 8, 64, 0.0, 0, L.F32, 0, None, 0, None) == L.EDTYPE
+    assert lib.b200k_fa2_fwd(one, one, one, one, 1, 1, 8, 64, 0.0, 1, L.BF16, 0, None, 0, None) == L.EARG   # bf16 + [B,H,D,N] V
+    assert lib.b200k_fa2_fwd(one, one, one, one, 1, 1, 8, 48, 0.0, 0, L.F16, 1, None, 0, None) == L.EHEADDIM
+    assert lib.b200k_gemm_ex(one, one, one, 12, 8, 8, 1, 0, L.F16, 0, None) == L.ESHAPE     # A^T storage: M % 8
+    assert lib.b200k_gemm_ex(one, one, one, 8, 8, 8, 1, 0, L.F32, 0, None) == L.EDTYPE
+    assert lib.b200k_transpose_u16_batched(one, None, 1, 4, 4, None) == L.EARG
+    assert lib.b200k_transpose_u16_batched(one, one, 0, 4, 4, None) == L.ESHAPE
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

@@ -215,3 +215,26 @@ def test_gemm_a_stored_transposed_nt_tt(shape, tn, dtype):
     ops.gemm(at.t().contiguous(), b, c2, variant=2 | (1 << 20))
     ops.gemm(at.t(), bb, c, tn=tn, a_km=True, variant=2 | (1 << 20))
     assert torch.equal(c, c2)
+
+
+@pytest.mark.parametrize("K", [64, 128, 192, 256, 320, 1024])
+@pytest.mark.parametrize("mn", [(512, 256), (1024, 768), (1000, 520), (2048, 2048)])
+def test_512x256_pair_tile_short_k_and_ragged(mn, K):
+    """The 512 x 256 tile (variant 4) issues the first min(4, k-blocks) k-blocks of a tile for accumulator block 0 alone,
+    then for block 1: exercise 1 ... 5 and many k-blocks, one and several tiles per pair, ragged M / N."""
+    from b200k import ops
+
+    M, N = mn
+    torch.manual_seed(M + K)
+    a = torch.randn(M, K, dtype=torch.half, device="cuda")
+    b = torch.randn(K, N, dtype=torch.half, device="cuda")
+    c = torch.full((M, N), float("nan"), dtype=torch.half, device="cuda")
+    ops.hgemm(a, b, c, variant=4)
+    want = a.double() @ b.double()
+    assert torch.isfinite(c).all()
+    assert (c.double() - want).abs().max() <= want.abs().max() * 2.0 ** -10
+    c2 = torch.empty_like(c)
+    ops.hgemm(a, b, c2, variant=2 | (1 << 20))     # 256 x 256 tile, no stream-K: same fp32 sums, same bits
+    assert torch.equal(c, c2)
+    ops.hgemm(a, b.t().contiguous().t(), c2, tn=True, variant=4)
+    assert torch.equal(c, c2)
