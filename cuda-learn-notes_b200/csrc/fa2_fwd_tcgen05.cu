@@ -35,15 +35,8 @@
 
 namespace b200k {
 
-template <int D_, int BC_, int STAGES_, bool V_DN_ = false, bool ALIAS_P_ = false, bool SHARE_S_ = false, int DT_ = 0,
-          bool SPLIT_S_ = false>
+template <int D_, int BC_, int STAGES_, bool V_DN_ = false, bool ALIAS_P_ = false, bool SHARE_S_ = false, int DT_ = 0>
 struct Fa2Cfg {
-  // SPLIT_S (with SHARE_S): the shared S buffer is handed over in two 64-key halves, each with its own full / free
-  // barrier.  The buffer is the serial resource of the D = 128 kernel - per KV tile it carries S_0 and S_1, each costing
-  // the QK^T MMAs (512 cycles) plus the softmax warps' tcgen05.ld (~600 cycles next to running MMAs) - so with whole-buffer
-  // hand-over the period cannot drop below ~2200 cycles against 2048 of tensor work.  In halves, the MMAs of one half run
-  // while the other half is being read out.
-  static constexpr bool SPLIT_S = SPLIT_S_;
   static constexpr int D = D_;
   static constexpr int DT = DT_;  // 0: fp16 Q/K/V/O and P; 1: bf16 (same kernel: kind::f16 with bf16 operand formats)
   static constexpr int BC = BC_;                       // keys per KV tile
@@ -58,7 +51,6 @@ struct Fa2Cfg {
   // also keeps their exponentials from competing for the MUFU pipe.
   static constexpr bool SHARE_S = SHARE_S_;
   static_assert(!(ALIAS_P && SHARE_S), "pick one");
-  static_assert(!SPLIT_S_ || (SHARE_S_ && BC_ == 128 && !V_DN_), "SPLIT_S is a refinement of SHARE_S");
   static constexpr bool V_DN = V_DN_;  // V passed transposed as [B,H,D,N] (the reference's *_swizzle_qkv entry points)
   static constexpr int CW = (D % 64 == 0) ? 64 : 32;  // width of one smem chunk along D (elements)
   static constexpr int NCH = D / CW;
@@ -264,25 +256,6 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           if (bar_b) umma_commit(bar_b);
         }
       };
-      // SPLIT_S: keys [64 h, 64 h + 64) of the tile -> S columns [64 h, 64 h + 64); waits for that half of the buffer
-      auto issue_s_half = [&](int i, int stage, int h, uint32_t wait_bar, uint32_t wait_parity, uint32_t bar_a, uint32_t bar_b) {
-        constexpr uint32_t idesc_h = make_idesc(128, 64, Cfg::DT, false, false);
-        const uint32_t q_addr = smem_q + i * Cfg::Q_TILE_BYTES;
-        const uint32_t k_addr = smem_k + stage * Cfg::KV_TILE_BYTES + h * 64 * ROWB;   // 64 key rows further inside every chunk
-        const uint32_t d_tmem = tmem_base + Cfg::S_COL0 + h * 64;
-        if (wait_bar) {
-          mbar_wait(wait_bar, wait_parity);
-          tc_fence_after();
-        }
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t q_off = (k / KSTEPS_PER_CHUNK) * Cfg::Q_CHUNK_BYTES + (k % KSTEPS_PER_CHUNK) * 32;
-          const uint32_t k_off = (k / KSTEPS_PER_CHUNK) * Cfg::KV_CHUNK_BYTES + (k % KSTEPS_PER_CHUNK) * 32;
-          umma_ss<1>(d_tmem, smem_desc(qk_hi, q_addr + q_off), smem_desc(qk_hi, k_addr + k_off), idesc_h, k != 0);
-        }
-        umma_commit(bar_a);
-        if (bar_b) umma_commit(bar_b);
-      };
       // O_i += P_i V.  P arrives in NP pieces of BC/NP keys (the softmax warps hand each piece over as soon as it is
       // written), so the first MMAs of PV_i(j) run under the exponentials of the later pieces.
       auto issue_pv = [&](int i, int stage, int j, uint32_t bar_a, uint32_t bar_b, uint32_t bar_c) {
@@ -312,35 +285,10 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(bar_q_full, 0);
       mbar_wait(bar_k_full, 0);
       tc_fence_after();
-      if constexpr (Cfg::SPLIT_S) {
-        issue_s_half(0, 0, 0, 0u, 0u, bar_s_full + 0, 0u);
-        issue_s_half(0, 0, 1, 0u, 0u, bar_s_full + 8, 0u);
-      } else {
-        issue_s(0, 0, bar_s_full, 0);
-      }
+      issue_s(0, 0, bar_s_full, 0);
       mbar_wait(bar_q_full + 8, 0);
       tc_fence_after();
-      if constexpr (Cfg::SPLIT_S) {
-        // barriers: s_full / s_free [2 i + h] for tile i, half h; everything else as in the SHARE_S loop below
-        for (int j = 0; j < T; ++j) {
-          const int s = j % STAGES, s1 = (j + 1) % STAGES, sp = (j + STAGES - 1) % STAGES;
-          issue_s_half(1, s, 0, bar_s_free + 0, j & 1, bar_s_full + 16, 0u);
-          issue_s_half(1, s, 1, bar_s_free + 8, j & 1, bar_s_full + 24, bar_k_empty + 8 * s);  // last reader of K(j)
-          if (j > 0) {
-            mbar_wait(bar_v_full + 8 * sp, ((j - 1) / STAGES) & 1);
-            issue_pv(1, sp, j - 1, bar_p_free + 8, 0u, bar_v_empty + 8 * sp);
-          }
-          if (j + 1 < T) {
-            mbar_wait(bar_k_full + 8 * s1, ((j + 1) / STAGES) & 1);
-            issue_s_half(0, s1, 0, bar_s_free + 16, j & 1, bar_s_full + 0, 0u);
-            issue_s_half(0, s1, 1, bar_s_free + 24, j & 1, bar_s_full + 8, 0u);
-          }
-          mbar_wait(bar_v_full + 8 * s, (j / STAGES) & 1);
-          issue_pv(0, s, j, bar_p_free, (j == T - 1) ? bar_o_full : 0u, 0u);
-        }
-        const int sl = (T - 1) % STAGES;
-        issue_pv(1, sl, T - 1, bar_p_free + 8, bar_o_full + 8, bar_v_empty + 8 * sl);
-      } else if constexpr (Cfg::SHARE_S) {
+      if constexpr (Cfg::SHARE_S) {
         // One S buffer, the two tiles half a period apart.  Issue order per KV tile j (each step waits only for what it
         // needs, and in steady state the waits are satisfied in exactly this order):
         //   S_1(j)     once tile 0's warps hold S_0(j) in registers            (s_free0)
@@ -537,20 +485,6 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int j = 0; j < T; ++j) {
       uint32_t sr[BC];
       const bool tw = TRACE && lane == 0 && q == 0;
-      if constexpr (Cfg::SPLIT_S) {
-        // the shared S buffer comes and goes in two 64-key halves (barriers [2 i + h])
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar_s_full + 8 * (2 * i + h), j & 1);
-          tc_fence_after();
-          tmem_ld_32x32b_x32(s_tmem + h * 64, sr + h * 64);
-          tmem_ld_32x32b_x32(s_tmem + h * 64 + 32, sr + h * 64 + 32);
-          tmem_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_s_free + 8 * (2 * i + h));
-        }
-      } else {
       mbar_wait(bar_s_full + 8 * i, j & 1);
       if (tw) tr(1 + i, j, 0);
       tc_fence_after();
@@ -563,7 +497,6 @@ fa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_s_free + 8 * i);
-      }
       }
       softmax_tile(j, sr);
     }
@@ -639,7 +572,7 @@ static int launch_fa2(const void* Q, const void* K, const void* V, void* O, int6
   unsigned long long* tbuf = nullptr;
   // Experiment / debug instantiations (piece counts, cycle trace, higher polynomial fractions) only exist for the two
   // benchmark shapes; every configuration has the production pair (POLY 0 and 1, two pieces).
-  constexpr bool kLab = (Cfg::D == 64 || Cfg::D == 128) && !Cfg::V_DN && Cfg::BC == 128 && Cfg::DT == 0 && !Cfg::SPLIT_S;
+  constexpr bool kLab = (Cfg::D == 64 || Cfg::D == 128) && !Cfg::V_DN && Cfg::BC == 128 && Cfg::DT == 0;
   // Pieces per KV tile in which P is handed to the MMA thread.  With the shared S buffer PV is off the critical chain
   // and one hand-over per tile is best (D = 128: 1 -> 1267, 2 -> 1209, 4 -> 1202 TFLOP/s); otherwise two.
   constexpr int DEF_NP = Cfg::SHARE_S ? 1 : 2;
@@ -747,8 +680,6 @@ extern "C" int b200k_fa2_fwd(const void* Q, const void* K, const void* V, void* 
       // 0x400: the older layout for D = 128 (P aliases S, S0 S1 O0 O1) instead of the shared S buffer
       if (variant & 0x400)
         return launch_fa2<Fa2Cfg<128, 128, 2, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly, mask);
-      if (variant & 0x40000)  // shared S buffer handed over in two 64-key halves
-        return launch_fa2<Fa2Cfg<128, 128, 2, false, false, true, 0, true>>(Q, K, V, O, B, H, N, scale, s, di, np, false, poly, mask);
       return launch_fa2<Fa2Cfg<128, 128, 2, false, false, true>>(Q, K, V, O, B, H, N, scale, s, di, np, trace, poly, mask);
   }
 }
