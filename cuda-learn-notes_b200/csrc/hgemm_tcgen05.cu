@@ -10,6 +10,9 @@
 //   warps 4..7  epilogue         tcgen05.ld 32 lanes x 64 columns -> fp16 -> swizzled smem -> TMA store, per warp
 // CG = 2 pairs two CTAs (cta_group::2, cluster 2x1x1) on one 256 x BN tile: each CTA loads its 128 rows of A and
 // its half of B; the leader CTA issues the MMAs for both and multicasts the commits.
+// Round 2: MT = 2 gives each CTA 256 rows (a 512 x 256 pair tile filling TMEM: a quarter less operand traffic per flop,
+// which on this power-limited part is clock frequency - see GemmCfg), a stream-K remainder round (GemmPlan), a pipelined
+// epilogue, A stored [K,M] as an MN-major operand (A_MN), and a %globaltimer trace hook.
 //
 // This replaces the reference's cp.async + ldmatrix + mma.sync.m16n8k16 kernels
 //   kernels/hgemm/mma/basic/hgemm_mma_stage.cu:L590-1023 (kernel), L2380-2454 (launcher)  and their NN/TN siblings;

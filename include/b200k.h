@@ -48,7 +48,10 @@ int b200k_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *       kernels/hgemm/cublas/hgemm_cublas.cu:L63-84 (hgemm_cublas_tensor_op_tn)
  * All matrices contiguous row-major; M,N,K >= 1; K % 8 == 0 and N % 8 == 0 (16-byte row pitch for TMA).
  * Ragged M/N/K (not multiples of the tile) are handled by TMA zero-fill / store clipping.
- * variant: 0 = auto; 1 = 1-CTA 128x256 tiles; 2 = 2-CTA (cta_group::2) 256x256 tiles; 3 = 2-CTA 256x128 tiles.
+ * variant (low 8 bits): 0 = auto; 1 = 1-CTA 128x256 tiles; 2 = 2-CTA (cta_group::2) 256x256 tiles, two accumulator buffers,
+ *   stream-K remainder round; 3 = 2-CTA 256x128 tiles; 4 = 2-CTA 512x256 tiles (auto picks it from ~3 rounds of them).
+ *   Higher bits are measurement switches (GROUP_M, L2 hints, bit 20 stream-K off, bit 21 keep 256x256), see hgemm_tcgen05.cu.
+ * Workspace: the stream-K round keeps one device workspace per (device, stream), cudaMalloc'ed on first use.
  */
 #define B200K_HGEMM_AUTO 0
 #define B200K_HGEMM_1CTA_128x256 1
