@@ -157,6 +157,22 @@ def ab_bench_protocol(f, sizes, rounds):
         del a, b, c
 
 
+def ncu_balance():
+    """One launch per configuration at 4096^3 and 8192^3 for `ncu --metrics sm__cycles_active.{min,max,avg}`: per-SM busy
+    cycles with and without the stream-K remainder round."""
+    for n in (4096, 8192):
+        a = torch.randn(n, n, dtype=torch.half, device="cuda")
+        b = torch.randn(n, n, dtype=torch.half, device="cuda")
+        c = torch.empty(n, n, dtype=torch.half, device="cuda")
+        for name, v in (("t256_streamk", V2), ("t256_static", V2 | SK_OFF), ("t512", 4)):
+            ops.hgemm(a, b, c, variant=v)
+            torch.cuda.synchronize()
+            print("NCU_ORDER %s_%d" % (name, n), flush=True)
+        torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        print("NCU_ORDER cublas_%d" % n, flush=True)
+
+
 def ncu_launches(n=8192):
     a = torch.randn(n, n, dtype=torch.half, device="cuda")
     b = torch.randn(n, n, dtype=torch.half, device="cuda")
@@ -182,5 +198,7 @@ if __name__ == "__main__":
             trace(f)
         elif what == "ab":
             ab_bench_protocol(f, [int(x) for x in sys.argv[2].split(",")], int(sys.argv[3]))
+        elif what == "balance":
+            ncu_balance()
         elif what == "ncu":
             ncu_launches()
