@@ -58,3 +58,12 @@ for D in (768, 1024):
     ops.ffpa_fwd(q, k, v, o)
 torch.cuda.synchronize()
 print("sanitize run (round 2 additions) done")
+# final round-2 additions: 512x256 tile with fewer k-blocks than ring stages, batched 16-bit transpose
+for K in (64, 192, 320):
+    a4 = torch.randn(1024, K, dtype=torch.half, device="cuda"); b4 = torch.randn(K, 520, dtype=torch.half, device="cuda")
+    c4 = torch.empty(1024, 520, dtype=torch.half, device="cuda")
+    ops.hgemm(a4, b4, c4, variant=4)
+xt = torch.randn(2, 3, 77, 130, dtype=torch.half, device="cuda"); yt = torch.empty(2, 3, 130, 77, dtype=torch.half, device="cuda")
+ops.transpose_16bit_batched(xt, yt)
+torch.cuda.synchronize()
+print("sanitize run (final additions) done")
