@@ -505,7 +505,7 @@ struct SkWorkspace {
 };
 static unsigned long long* g_hgemm_trace = nullptr;  // b200k_debug_set_hgemm_trace()
 
-static int get_sk_workspace(int device, cudaStream_t stream, size_t partial_bytes, SkWorkspace** out) {
+static int get_sk_workspace(int device, cudaStream_t stream, size_t partial_bytes, SkWorkspace* out) {
   static std::mutex mu;
   static std::map<std::pair<int, cudaStream_t>, SkWorkspace> table;
   constexpr size_t kFlagBytes = 4096;  // 128 clusters x 2 CTAs x 4 warps x 4 B
@@ -522,7 +522,7 @@ static int get_sk_workspace(int device, cudaStream_t stream, size_t partial_byte
     w.partial_bytes = partial_bytes;
   }
   ++w.epoch;
-  *out = &w;
+  *out = w;   // a copy taken under the lock: pointers and this launch's epoch
   return B200K_OK;
 }
 
@@ -558,15 +558,15 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   if (Cfg::NACC == 2 && rem_tiles != 0 && (num_tiles > max_clusters || force_sk) && num_kb >= 8 && max_clusters <= 128 &&
       !((tune >> 20) & 1)) {
     const int64_t units = rem_tiles * num_kb;
-    SkWorkspace* ws = nullptr;
+    SkWorkspace ws;
     if ((rc = get_sk_workspace(di.device, stream, size_t(max_clusters) * Cfg::CG * Cfg::BM_CTA * Cfg::BN * sizeof(float), &ws))) return rc;
     clusters = max_clusters;
     plan.sk_tiles = int(rem_tiles);
     plan.units_lo = int(units / clusters);
     plan.units_rem = int(units % clusters);
-    plan.epoch = ws->epoch;
-    plan.partials = ws->partials;
-    plan.flags = ws->flags;
+    plan.epoch = ws.epoch;
+    plan.partials = ws.partials;
+    plan.flags = ws.flags;
   }
   // tune (experiments): bits [8,16) override GROUP_M, bits [16,20) select the L2 eviction hints of the TMA loads.
   int group_m = 8;
