@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call A: stream-K correctness, full GPU suite, HGEMM trace / round-robin timing / DRAM-traffic sweep, reference scripts
-cd $(dirname "$0")/..
+cd $(dirname "$0")/../..
 O=gpurun_out/r2; mkdir -p $O
 timeout 300 python tools/gpu_hgemm_r2.py check > $O/hgemm_check.log 2>&1; echo "check rc=$?"; grep -c '"ok": true' $O/hgemm_check.log; grep '"ok": false' $O/hgemm_check.log | head -5; grep check_tn $O/hgemm_check.log | grep -c 'true'
 timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -15

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd $(dirname "$0")/..
+cd $(dirname "$0")/../..
 O=gpurun_out/r2; mkdir -p $O
 timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -40
 cat > /tmp/two.py <<'PY'

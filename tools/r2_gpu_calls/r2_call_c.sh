@@ -1,5 +1,5 @@
 #!/bin/bash
-cd $(dirname "$0")/..
+cd $(dirname "$0")/../..
 O=gpurun_out/r2; mkdir -p $O
 timeout 300 python tools/gpu_hgemm_r2.py check > $O/hgemm_check2.log 2>&1; echo "check rc=$?"; grep -c '"ok": true' $O/hgemm_check2.log; grep '"ok": false' $O/hgemm_check2.log | head -5; tail -3 $O/hgemm_check2.log | cut -c1-300
 timeout 600 python -m pytest tests -m gpu -q > $O/pytest_c.log 2>&1; tail -8 $O/pytest_c.log; grep -n "Error\|assert " $O/pytest_c.log | head -20

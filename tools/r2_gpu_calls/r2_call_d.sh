@@ -1,5 +1,5 @@
 #!/bin/bash
-cd $(dirname "$0")/..
+cd $(dirname "$0")/../..
 O=gpurun_out/r2; mkdir -p $O
 timeout 300 python tools/gpu_hgemm_r2.py check > $O/hgemm_check3.log 2>&1; echo "check rc=$?"; grep -c '"ok": true' $O/hgemm_check3.log; grep '"ok": false' $O/hgemm_check3.log | head -5 | cut -c1-400
 timeout 900 python -m pytest tests -m gpu -q > $O/pytest_d.log 2>&1; tail -12 $O/pytest_d.log

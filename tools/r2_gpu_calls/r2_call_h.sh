@@ -1,5 +1,5 @@
 #!/bin/bash
-cd $(dirname "$0")/..
+cd $(dirname "$0")/../..
 O=gpurun_out/r2; mkdir -p $O
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench_n1_c.json 2> $O/bench_n1_c.err; echo "bench rc=$?"; tail -c 400 $O/bench_n1_c.err

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd $(dirname "$0")/..
+cd $(dirname "$0")/../..
 O=gpurun_out/r2; mkdir -p $O
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 1200 python -m pytest tests -m gpu -q > $O/pytest_j.log 2>&1; tail -4 $O/pytest_j.log

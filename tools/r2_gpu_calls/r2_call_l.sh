@@ -1,5 +1,5 @@
 #!/bin/bash
-cd $(dirname "$0")/..
+cd $(dirname "$0")/../..
 O=gpurun_out/r2; mkdir -p $O
 timeout 300 python tools/gpu_hgemm_r2.py check > $O/hgemm_check5.log 2>&1; echo "check rc=$?"; grep -c '"ok": true' $O/hgemm_check5.log; grep '"ok": false' $O/hgemm_check5.log | head -3 | cut -c1-300
 timeout 600 python -m pytest tests/test_gpu_hgemm.py tests/test_abi.py -q 2>&1 | tail -3

@@ -1,6 +1,6 @@
 #!/bin/bash
 # multi-GPU bench, sharded section only.  usage: r2_call_mg.sh N
-cd $(dirname "$0")/..
+cd $(dirname "$0")/../..
 N=$1
 O=gpurun_out/r2; mkdir -p $O
 NCCL_DEBUG=INFO timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 --sections sharded > $O/bench_n${N}_sharded.json 2> $O/bench_n${N}_sharded.err; echo "bench rc=$?"

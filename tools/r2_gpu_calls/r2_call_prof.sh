@@ -1,5 +1,5 @@
 #!/bin/bash
-cd $(dirname "$0")/..
+cd $(dirname "$0")/../..
 O=gpurun_out/r2; mkdir -p $O
 NCU="ncu --set full --clock-control none --import-source on"
 timeout 600 $NCU -k regex:hgemm_tcgen05 -s 3 -c 1 -o $O/prof_hgemm_8192 python tools/prof_run.py hgemm 8192 8192 8192 > $O/prof1.log 2>&1; echo "ncu hgemm rc=$?"
