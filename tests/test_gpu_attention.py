@@ -88,7 +88,8 @@ def test_fa2_experiment_builds_agree_with_oracle(D, variant):
     assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), **TOL)
 
 
-@pytest.mark.parametrize("D,variant", [(256, 32), (256, 2), (256, 4), (256, 8), (512, 1), (512, 2), (512, 33), (320, 32)])
+@pytest.mark.parametrize("D,variant", [(256, 32), (256, 2), (256, 4), (256, 8), (512, 1), (512, 2), (512, 33), (320, 32),
+                                       (512, 0x400), (256, 0x200), (512, 0x200)])
 def test_ffpa_selectable_builds_agree_with_oracle(D, variant):
     """The non-default FFPA builds (two threads per row, streamed Q, serial issue order, forced 1-CTA / CTA-pair)
     stay correct: they are the fallbacks and the A/B baselines the design notes quote."""
@@ -238,3 +239,51 @@ def test_ffpa_every_ladder_rung(D):
     q, k, v = [torch.randn(1, 2, 300, D, dtype=torch.half, device="cuda") for _ in range(3)]
     o = _run(q, k, v)
     assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), **TOL)
+
+
+@pytest.mark.parametrize("D", [256, 512])
+@pytest.mark.parametrize("N", [1, 63, 128, 255, 256, 257, 511, 1000, 2304])
+def test_ffpa_otrans_kernel_shapes(D, N):
+    """The O^T kernel (ffpa3_fwd_tcgen05.cu; default for D = 512, variant 0x200 elsewhere): one, two and many 256-key
+    tiles, ragged in both halves of the folded score tile, several heads, against the oracle and the D-sliced kernel."""
+    from b200k import ops
+
+    torch.manual_seed(N * 7 + D)
+    q, k, v = [torch.randn(2, 3, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.full_like(q, float("nan"))
+    ops.ffpa_fwd(q, k, v, o, variant=0x200)
+    assert torch.isfinite(o).all()
+    assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), **TOL)
+    o2 = torch.empty_like(o)
+    ops.ffpa_fwd(q, k, v, o2, variant=0x400 if D == 512 else 0)
+    assert torch.allclose(o.float(), o2.float(), rtol=1e-2, atol=1e-3)
+    ones = torch.ones_like(v)
+    ops.ffpa_fwd(q, k, ones, o, variant=0x200)
+    assert torch.equal(o, ones)
+
+
+@pytest.mark.parametrize("D", [256, 512])
+def test_ffpa_otrans_cross_cta_rescale(D):
+    """Scores that grow along the key axis move the reference max of some rows by more than 2^8 in several tiles; the rows
+    of one CTA of the pair only (rows 0-63 of every 128) to exercise a rescale requested by the peer, then all rows."""
+    from b200k import ops
+
+    torch.manual_seed(11 + D)
+    B, H, N = 1, 2, 1536
+    q = torch.randn(B, H, N, D, dtype=torch.half, device="cuda")
+    v = torch.randn(B, H, N, D, dtype=torch.half, device="cuda")
+    base = torch.randn(B, H, N, D, device="cuda") * 0.1
+    qdir = q[:, :, :1].float() / q[:, :, :1].float().norm(dim=-1, keepdim=True)
+    ramp = torch.linspace(0, 90, N, device="cuda").view(1, 1, N, 1)
+    k = (base + ramp * qdir * 0.4).half()
+    for rows in ("all", "first_half_of_each_tile"):
+        qq = q.clone()
+        if rows == "first_half_of_each_tile":
+            idx = torch.arange(N, device="cuda")
+            qq[:, :, (idx % 128) >= 64] *= 0.01          # these rows see flat scores: only the peer CTA's rows move
+        qq[:, :, :, :] = qq + 4.0 * qdir.half()           # every active row is pulled along the ramp direction
+        o = torch.full_like(qq, float("nan"))
+        ops.ffpa_fwd(qq, k, v, o, variant=0x200)
+        want = oracle.attention(qq, k, v).float()
+        assert torch.isfinite(o).all()
+        assert torch.allclose(o.cpu().float(), want, **TOL), rows
