@@ -34,9 +34,12 @@ constexpr int KBOX = 128 * 128;    // [128 keys x 64 fp16]: this CTA's half of a
 constexpr int VBOX = 128 * 128;    // [128 keys x 64 head-dim columns]
 constexpr int PBOX = 64 * 128;     // [64 rows x 64 keys]
 constexpr int STAGE_BYTES = 32768; // 2 K half-chunks, or the 2 V boxes of one accumulator for 128 keys
-constexpr int BAR_BYTES = 1024;
-constexpr int MISC_BYTES = 4096;   // xchg[2][128] f32 | alpha[4][128] f32 | linv[128] f32 | flags[4][4] u32 | decision[4] u32
-constexpr int MAX_STAGES = 4;
+// Every byte of shared memory counts: the operand ring must keep ~64 B/clk of K and V in flight against an L2 latency of
+// ~1.5 us, and with Q (64 KB) and P (32 KB) resident a fourth 32 KB stage only fits if the bookkeeping stays inside 3 KB and
+// the dynamic shared memory needs no alignment slack (it starts 1 KB into the window; the kernel checks).
+constexpr int BAR_BYTES = 256;
+constexpr int MISC_BYTES = 2816;   // xchg[2][128] f32 (2nd half doubles as 1/l at the end) | alpha[3][128] f32 | flags[4][4] | decision[4]
+constexpr int MAX_STAGES = 6;
 constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256;
 constexpr int TMEM_COLS = 512;
 constexpr int THREADS = 256;
@@ -58,6 +61,11 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
 }
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// Remote arrive WITHOUT release semantics: for hand-shakes that order nothing but tensor-memory reads (the tcgen05 fence
+// before it does that).  The .release.cluster form costs a cluster-wide memory fence per arrive (MEMBAR + ERRBAR in SASS).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // wait with cluster-scope acquire: data written by the peer CTA before its release.cluster arrive is visible afterwards
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -85,10 +93,10 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
   using namespace ffpa3;
   constexpr int D = 256 * NACC;
   constexpr int nqk = D / CW;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();   // the swizzled operand tiles need 1024-byte alignment and there is no slack to realign
+  uint8_t* base_ptr = smem_raw;
 
   const uint32_t bar_full = base;                          // MAX_STAGES (leader's are used)
   const uint32_t bar_empty = base + 8 * MAX_STAGES;        // MAX_STAGES (each CTA its own, multicast commits)
@@ -104,10 +112,10 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
   const uint32_t misc = base + BAR_BYTES;
   const uint32_t xchg = misc;                 // [2][128] f32: partial row maxima / row sums of the two half-row threads
-  const uint32_t alpha_buf = misc + 1024;     // [4][128] f32: rescale factor of every row of the pair, tile j in slot j & 3
-  const uint32_t linv_buf = misc + 3072;      // [128] f32: 1 / row sum
-  const uint32_t flag_buf = misc + 3584;      // [4][4] u32: "a row of warp w of CTA c moved its max" (c*2 + w)
-  const uint32_t decision_buf = misc + 3648;  // [4] u32: the MMA thread's verdict for tile j (slot j & 3)
+  const uint32_t alpha_buf = misc + 1024;     // [3][128] f32: rescale factor of every row of the pair, tile j in slot j % 3
+  const uint32_t linv_buf = misc + 512;       // [128] f32: 1 / row sum (the second xchg slot, dead by then)
+  const uint32_t flag_buf = misc + 2560;      // [4][4] u32: "a row of warp w of CTA c moved its max" (c*2 + w)
+  const uint32_t decision_buf = misc + 2624;  // [4] u32: the MMA thread's verdict for tile j (slot j & 3)
   const uint32_t smem_q = misc + MISC_BYTES;
   const uint32_t smem_p = smem_q + nqk * QBOX;            // ONE buffer of 4 chunks x PBOX (64 rows x 256 keys)
   const uint32_t smem_ring = smem_p + 4 * PBOX;
@@ -287,7 +295,7 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
     const uint32_t lane_base = (q * 32) << 16;
     float m_ref = -INFINITY;
     float l = 0.f;
-    auto apply_decision = [&](int t) {   // t = tile whose factors are in slot t & 3
+    auto apply_decision = [&](int t) {   // t = tile whose factors are in slot t % 3
       mbar_wait_cluster(bar_decision + 8 * (t & 1), (t >> 1) & 1);
       if (ld_shared_u32(decision_buf + (t & 3) * 4) != 0) {
         if (t >= 1) {  // O^T must be stable: PV(t-1) complete (PV(t) is held back by the MMA thread until this is done)
@@ -302,7 +310,7 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
             tmem_wait_ld();
 #pragma unroll
             for (int e = 0; e < 16; ++e)
-              orr[e] = __float_as_uint(__uint_as_float(orr[e]) * ld_shared_f32(alpha_buf + ((t & 3) * 128 + c * 16 + e) * 4));
+              orr[e] = __float_as_uint(__uint_as_float(orr[e]) * ld_shared_f32(alpha_buf + ((t % 3) * 128 + c * 16 + e) * 4));
             tmem_st_32x32b_x16(o_tmem + c * 16, orr);
           }
         }
@@ -326,7 +334,7 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(bar_s_free + 8 * buf, 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa(bar_s_free + 8 * buf, 0));
       float* s = reinterpret_cast<float*>(sr);
       if (j == T - 1 && (N % BC) != 0) {
         asm volatile("" ::: "memory");
@@ -355,7 +363,7 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
       // publish this row's factor (one of the two threads of the row) and the warp's "moved" flag to both CTAs; nobody
       // waits here: the release of the p_full arrive below makes them visible to the MMA thread and to the peer
       if (h == 0) {
-        const uint32_t a_addr = alpha_buf + ((j & 3) * 128 + grow) * 4;
+        const uint32_t a_addr = alpha_buf + ((j % 3) * 128 + grow) * 4;
         st_shared_f32(a_addr, alpha);
         st_shared_cluster_u32(mapa(a_addr, peer), __float_as_uint(alpha));
       }
@@ -411,16 +419,17 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
     }
     apply_decision(T - 1);
     // ---- epilogue: row sums of the two half-row threads -> 1 / l for every row of the pair, in both CTAs
+    named_bar_sync(1, 128);                 // every local thread is done with the exchange slots of the last tile
     st_shared_f32(xchg + L * 4, l);
     named_bar_sync(1, 128);
+    mbar_wait(bar_o_full, 0);               // the last PV has run: both CTAs are past every read of the second exchange slot
+    tc_fence_after();
     if (h == 0) {
       const float inv = 1.0f / (l + ld_shared_f32(xchg + (L ^ 64u) * 4));
       const uint32_t a_addr = linv_buf + grow * 4;
       st_shared_f32(a_addr, inv);
       st_shared_cluster_u32(mapa(a_addr, peer), __float_as_uint(inv));
     }
-    mbar_wait(bar_o_full, 0);
-    tc_fence_after();
     // cluster barrier #1 (all threads of both CTAs take part, the other warps below): every 1 / l written by the peer is visible
     cluster_sync();
     // O[q0 + c, a*256 + rank*128 + L] = O^T[L][c] / l[c]
@@ -460,7 +469,7 @@ int launch_ffpa_otrans(const void* Q, const void* K, const void* V, void* O, int
   int device = 0;
   B200K_CHECK_CUDA(cudaGetDevice(&device));
   const int nacc = int(D / 256);
-  const int fixed = 1024 + ffpa3::BAR_BYTES + ffpa3::MISC_BYTES + int(D / 64) * ffpa3::QBOX + 4 * ffpa3::PBOX;
+  const int fixed = ffpa3::BAR_BYTES + ffpa3::MISC_BYTES + int(D / 64) * ffpa3::QBOX + 4 * ffpa3::PBOX;
   int stages = (232448 - fixed) / ffpa3::STAGE_BYTES;
   if (stages > ffpa3::MAX_STAGES) stages = ffpa3::MAX_STAGES;
   const int smem = fixed + stages * ffpa3::STAGE_BYTES;

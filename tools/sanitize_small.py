@@ -67,3 +67,10 @@ xt = torch.randn(2, 3, 77, 130, dtype=torch.half, device="cuda"); yt = torch.emp
 ops.transpose_16bit_batched(xt, yt)
 torch.cuda.synchronize()
 print("sanitize run (final additions) done")
+# the O^T FFPA kernel (default at D = 512, variant 0x200 at D = 256), incl. a ragged two-tile case
+for D, N in ((512, 300), (256, 257), (512, 64)):
+    q, k, v = [torch.randn(1, 2, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    o = torch.empty_like(q)
+    ops.ffpa_fwd(q, k, v, o, variant=0x200)
+torch.cuda.synchronize()
+print("sanitize run (O^T FFPA) done")
