@@ -641,7 +641,7 @@ def main():
             fl = 4.0 * B_ * H_ * N_ * N_ * D_
             t = cuda_time(lambda: fn(q, k, v, o), 10, 3)
             r = {"shape": list(shape), "ms": t, "tflops": fl / t * 1e-9, "frac_of_peak_burst": fl / t * 1e-9 / peaks["tflops_burst"]}
-            rooflines[tag] = roofline_obj(("fa2_fwd_tcgen05_kernel" if D_ <= 128 else "ffpa2_fwd_tcgen05_kernel") + " " + tag, fl, t, peaks,
+            rooflines[tag] = roofline_obj(("fa2_fwd_tcgen05_kernel" if D_ <= 128 else "ffpa3_fwd_tcgen05_kernel<2>") + " " + tag, fl, t, peaks,
                                           tag, 4.0 * B_ * H_ * N_ * D_ * 2, t * 10)
             if ref_fa is not None and D_ <= 128:
                 try:

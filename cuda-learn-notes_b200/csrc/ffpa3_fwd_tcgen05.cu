@@ -67,6 +67,24 @@ __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// Arrives that publish only (a) this CTA's own shared memory to its own tensor core and (b) words that travel with
+// st.async below: release at CTA scope is all they need.  The .release.cluster form costs a GPU-wide memory fence
+// (MEMBAR.ALL.GPU + ERRBAR, ~1-1.5 k cycles measured) and sat on the softmax -> PV chain of every tile.
+__device__ __forceinline__ void mbar_arrive_cluster_release_cta(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster_release_cta(uint32_t cluster_bar, uint32_t tx) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(tx) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster_relaxed(uint32_t cluster_bar, uint32_t tx) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(tx) : "memory");
+}
+// One 32-bit word into a CTA of the cluster, completing 4 bytes on an mbarrier of THAT CTA: whoever sees the barrier phase
+// complete sees the word - no fence on either side.
+__device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v), "r"(cluster_bar)
+               : "memory");
+}
 // wait with cluster-scope acquire: data written by the peer CTA before its release.cluster arrive is visible afterwards
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -271,11 +289,13 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
           // did any row of the pair move its reference max in tile j?  (flags written by all 8 warps before their arrive)
           const uint32_t fb = flag_buf + (j & 3) * 16;
           const uint32_t f = ld_shared_u32(fb) | ld_shared_u32(fb + 4) | ld_shared_u32(fb + 8) | ld_shared_u32(fb + 12);
+          // the verdict and the 128 rescale factors of tile j (st.async by the softmax threads) complete on the same barrier
           const uint32_t d_addr = decision_buf + (j & 3) * 4;
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(d_addr), "r"(f) : "memory");
-          st_shared_cluster_u32(mapa(d_addr, 1), f);
-          mbar_arrive_cluster(mapa(bar_decision + 8 * (j & 1), 0));
-          mbar_arrive_cluster(mapa(bar_decision + 8 * (j & 1), 1));
+          for (uint32_t c = 0; c < 2; ++c) {
+            const uint32_t db = mapa(bar_decision + 8 * (j & 1), c);
+            mbar_arrive_expect_tx_cluster_relaxed(db, 4 + 128 * 4);
+            st_async_u32(mapa(d_addr, c), f, db);
+          }
           if (f != 0) {
             mbar_wait_cluster(bar_rsdone, rs_phase);
             rs_phase ^= 1;
@@ -360,19 +380,13 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
           l *= alpha;
         }
       }
-      // publish this row's factor (one of the two threads of the row) and the warp's "moved" flag to both CTAs; nobody
-      // waits here: the release of the p_full arrive below makes them visible to the MMA thread and to the peer
+      // publish this row's factor (one of the two threads of the row) to both CTAs: st.async completing on the decision
+      // barrier of tile j, which every reader of the factors waits on.  Nobody waits here.
       if (h == 0) {
         const uint32_t a_addr = alpha_buf + ((j % 3) * 128 + grow) * 4;
-        st_shared_f32(a_addr, alpha);
-        st_shared_cluster_u32(mapa(a_addr, peer), __float_as_uint(alpha));
+        for (uint32_t c = 0; c < 2; ++c) st_async_u32(mapa(a_addr, c), __float_as_uint(alpha), mapa(bar_decision + 8 * buf, c));
       }
       const uint32_t any = __any_sync(0xffffffffu, need) ? 1u : 0u;
-      if (lane == 0 && q < 2) {
-        const uint32_t f_addr = flag_buf + ((j & 3) * 4 + rank * 2 + q) * 4;
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(f_addr), "r"(any) : "memory");
-        st_shared_cluster_u32(mapa(f_addr, peer), any);
-      }
       // P = exp2(s * scale - m_ref) for this thread's 128 keys
       float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
       const float neg_m = -m_ref;
@@ -415,7 +429,15 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(bar_p_full + 8 * buf, 0));
+      if (lane == 0) {
+        const uint32_t pf = mapa(bar_p_full + 8 * buf, 0);
+        if (q < 2) {   // the two threads of a row agree on "moved": the warps of the first half-row carry the flag
+          mbar_arrive_expect_tx_cluster_release_cta(pf, 4);
+          st_async_u32(mapa(flag_buf + ((j & 3) * 4 + rank * 2 + q) * 4, 0), any, pf);
+        } else {
+          mbar_arrive_cluster_release_cta(pf);
+        }
+      }
     }
     apply_decision(T - 1);
     // ---- epilogue: row sums of the two half-row threads -> 1 / l for every row of the pair, in both CTAs
