@@ -311,7 +311,7 @@ ffpa2_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(bar_p_full + 8 * buf, 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa(bar_p_full + 8 * buf, 0));   // P is in TMEM (wait::st above): nothing else to publish
     }
     // ---- epilogue: this CTA's 128 rows x 256 columns
     mbar_wait(bar_o_full, 0);

@@ -62,11 +62,6 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-// Remote arrive WITHOUT release semantics: for hand-shakes that order nothing but tensor-memory reads (the tcgen05 fence
-// before it does that).  The .release.cluster form costs a cluster-wide memory fence per arrive (MEMBAR + ERRBAR in SASS).
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
 // Arrives that publish only (a) this CTA's own shared memory to its own tensor core and (b) words that travel with
 // st.async below: release at CTA scope is all they need.  The .release.cluster form costs a GPU-wide memory fence
 // (MEMBAR.ALL.GPU + ERRBAR, ~1-1.5 k cycles measured) and sat on the softmax -> PV chain of every tile.

@@ -457,7 +457,7 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_cluster(mapa(bar_tempty + 8 * which, 0));
+          if constexpr (CG == 2) mbar_arrive_cluster_relaxed(mapa(bar_tempty + 8 * which, 0));   // only TMEM reads, already complete
           else mbar_arrive(bar_tempty + 8 * which);
         }
       };

@@ -92,6 +92,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// Remote arrive WITHOUT release semantics, for hand-shakes that order nothing but tensor-memory accesses which have already
+// completed (tcgen05.wait::ld / ::st + tcgen05.fence::before_thread_sync in front of it).  The .release.cluster form costs a
+// GPU-wide memory fence per arrive (MEMBAR.ALL.GPU + ERRBAR in SASS, 1-1.5 k cycles measured inside the FFPA O^T kernel).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }

@@ -53,7 +53,7 @@ def main():
 
     cases = []
     # hgemm 8192^3 and 4096^3 (variant auto)
-    for n in (4096, 8192):
+    for n in (2048, 4096, 8192):
         a = torch.randn(n, n, device=dev, dtype=torch.float16)
         b = torch.randn(n, n, device=dev, dtype=torch.float16)
         c = torch.empty(n, n, device=dev, dtype=torch.float16)
@@ -66,12 +66,14 @@ def main():
         cases.append(("fa2_d%d" % D, 4.0 * B * H * N * N * D, 5,
                       lambda lib, st, q=q, k=k, v=v, o=o, s=(B, H, N, D): lib.b200k_fa2_fwd_f16(
                           q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), *s, 0.0, 0, 0, st)))
-    for (B, H, N, D) in ((1, 32, 8192, 256), (1, 32, 8192, 512), (1, 32, 8192, 1024), (1, 32, 8192, 320)):
+    # variant 0x400 at D = 512: the D-sliced CTA-pair kernel (the default there is the O^T kernel)
+    for (B, H, N, D, var) in ((1, 32, 8192, 256, 0), (1, 32, 4096, 512, 0), (1, 32, 4096, 512, 0x400), (1, 32, 4096, 768, 0),
+                              (1, 32, 4096, 1024, 0), (1, 32, 8192, 320, 0)):
         q, k, v = (torch.randn(B, H, N, D, device=dev, dtype=torch.float16) for _ in range(3))
         o = torch.empty_like(q)
-        cases.append(("ffpa_d%d" % D, 4.0 * B * H * N * N * D, 5,
-                      lambda lib, st, q=q, k=k, v=v, o=o, s=(B, H, N, D): lib.b200k_ffpa_fwd_f16(
-                          q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), *s, 0.0, 0, st)))
+        cases.append(("ffpa_d%d_v%x" % (D, var), 4.0 * B * H * N * N * D, 5,
+                      lambda lib, st, q=q, k=k, v=v, o=o, s=(B, H, N, D), var=var: lib.b200k_ffpa_fwd_f16(
+                          q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), *s, 0.0, var, st)))
     if args.only:
         cases = [c for c in cases if args.only in c[0]]
 
