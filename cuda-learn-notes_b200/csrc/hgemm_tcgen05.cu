@@ -87,7 +87,7 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 // pairs).  Those r tiles are done stream-K instead: their r * KB k-blocks are cut into G contiguous, equal ranges, one
 // per cluster, processed BEFORE the cluster's data-parallel tiles.  A range is shorter than one tile (r < G), so it
 // touches at most two tiles: the tail k-blocks of tile j ("writer": fp32 partial sums go to a workspace slot owned by
-// the cluster, then a per-warp flag is set to this launch's epoch) and the head k-blocks of tile j+1 ("finisher": it
+// the cluster, then a per-warp flag is raised) and the head k-blocks of tile j+1 ("finisher": it
 // holds k-block 0, runs second, and its epilogue adds the partials of the clusters that follow it before converting and
 // storing).  Sums are added in a fixed order, so results are deterministic.  All clusters are co-resident (grid <= #SMs,
 // one CTA per SM), which is what lets a finisher wait for its writers.
@@ -95,9 +95,8 @@ struct GemmPlan {
   int sk_tiles = 0;       // r: tiles [0, r) are stream-K
   int units_lo = 0;       // every cluster gets units_lo k-blocks of the r * KB, the first units_rem get one more
   int units_rem = 0;
-  uint32_t epoch = 0;     // value a writer's flag takes in this launch
   float* partials = nullptr;   // [cluster][cta rank][epilogue warp][32 rows x BN] fp32, layout private to the kernel
-  uint32_t* flags = nullptr;   // [cluster][cta rank][epilogue warp]
+  uint32_t* flags = nullptr;   // [cluster][cta rank][epilogue warp]: 0 = empty, 1 = partial published; the reader lowers it again
   unsigned long long* trace = nullptr;  // debugging: globaltimer stamps, 128 per cluster (b200k_debug_set_hgemm_trace)
 };
 
@@ -382,13 +381,17 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr int NCHUNK = Cfg::MT * (BN / CC);
       const size_t my_slot = (size_t(cluster_id) * CG + cta_rank) * 4 + q;
       if (w.kind == 2) {
-        // finisher: wait until every writer of this tile has published this warp's slice (flag == epoch)
+        // finisher: wait until every writer of this tile has published this warp's slice, then lower the flag again (each
+        // slot has exactly one reader and is written at most once per launch), so that every launch - and every replay
+        // of a CUDA graph that captured one - starts from all-zero flags without anything host-side
         for (int cc = cluster_id + 1; cc <= w.last_writer; ++cc) {
-          const volatile uint32_t* f = plan.flags + (size_t(cc) * CG + cta_rank) * 4 + q;
+          volatile uint32_t* f = plan.flags + (size_t(cc) * CG + cta_rank) * 4 + q;
           const long long t0 = clock64();
-          while (*f != plan.epoch) {
+          while (*f == 0u) {
             if (clock64() - t0 > B200K_SPIN_LIMIT_CYCLES) __trap();
           }
+          __syncwarp();   // every lane has seen the flag
+          if (lane == 0) *f = 0u;
         }
         __threadfence();
       }
@@ -479,7 +482,7 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // publish: all lanes' partial stores, then the flag (the finisher's matching warp polls it)
         __threadfence();
         __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(plan.flags + my_slot) = plan.epoch;
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(plan.flags + my_slot) = 1u;
       }
       if (trace && leader && warp == 4 && it < 56 && lane == 0) trace[64 + it] = global_timer();
     }
@@ -494,14 +497,14 @@ hgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 // Stream-K workspace: one per (device, stream), allocated on first use and kept (like a BLAS handle's workspace), so
-// that launches on different streams never share partial sums.  Flags are compared against a per-workspace launch
-// counter ("epoch"), so nothing has to be cleared between launches.  First use on a stream calls cudaMalloc: warm up
-// before capturing a CUDA graph.
+// that launches on different streams never share partial sums.  Flags are zeroed at allocation and lowered by their
+// reader inside the kernel, so nothing has to be cleared between launches and a captured launch can be replayed.  First
+// use on a stream (or a larger problem than any before on it) calls cudaMalloc: warm up on the capture stream, at the
+// largest size, before capturing a CUDA graph.
 struct SkWorkspace {
   float* partials = nullptr;
   uint32_t* flags = nullptr;
   size_t partial_bytes = 0;
-  uint32_t epoch = 0;
 };
 static unsigned long long* g_hgemm_trace = nullptr;  // b200k_debug_set_hgemm_trace()
 
@@ -521,8 +524,7 @@ static int get_sk_workspace(int device, cudaStream_t stream, size_t partial_byte
     w.flags = reinterpret_cast<uint32_t*>(static_cast<char*>(p) + partial_bytes);
     w.partial_bytes = partial_bytes;
   }
-  ++w.epoch;
-  *out = w;   // a copy taken under the lock: pointers and this launch's epoch
+  *out = w;   // a copy taken under the lock
   return B200K_OK;
 }
 
@@ -564,7 +566,6 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
     plan.sk_tiles = int(rem_tiles);
     plan.units_lo = int(units / clusters);
     plan.units_rem = int(units % clusters);
-    plan.epoch = ws.epoch;
     plan.partials = ws.partials;
     plan.flags = ws.flags;
   }

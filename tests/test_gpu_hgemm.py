@@ -238,3 +238,40 @@ def test_512x256_pair_tile_short_k_and_ragged(mn, K):
     assert torch.equal(c, c2)
     ops.hgemm(a, b.t().contiguous().t(), c2, tn=True, variant=4)
     assert torch.equal(c, c2)
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096, 1024), (2304, 3072, 512)])
+def test_stream_k_launch_replays_under_cuda_graph(shape):
+    """ONE stream-K launch (more 256 x 256 tiles than CTA pairs, with a remainder round) captured into a CUDA graph and
+    replayed with new operand contents: the writer -> finisher flags are lowered by their reader inside the kernel, so a
+    replay starts from the same state as a fresh launch (a host-side launch counter would be frozen into the graph).
+    Warm-up runs on the capture stream first: the stream-K workspace is allocated on first use per stream."""
+    from b200k import _loader as L
+    from b200k import ops
+
+    M, N, K = shape
+    torch.manual_seed(7)
+    a = torch.randn(M, K, dtype=torch.half, device="cuda")
+    b = torch.randn(K, N, dtype=torch.half, device="cuda")
+    c = torch.empty(M, N, dtype=torch.half, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            ops.hgemm(a, b, c, variant=L.HGEMM_2CTA_256x256)
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        ops.hgemm(a, b, c, variant=L.HGEMM_2CTA_256x256)
+    for rep in range(4):
+        a.copy_(torch.randn(M, K, dtype=torch.half, device="cuda"))
+        torch.cuda.synchronize()
+        c.fill_(float("nan"))
+        g.replay()
+        torch.cuda.synchronize()
+        eager = torch.empty_like(c)
+        ops.hgemm(a, b, eager, variant=L.HGEMM_2CTA_256x256)
+        torch.cuda.synchronize()
+        assert torch.equal(c, eager), rep                      # same kernel, same fixed summation order
+        want = a.double() @ b.double()
+        assert (c.double() - want).abs().max() <= want.abs().max() * 2.0 ** -9, rep
