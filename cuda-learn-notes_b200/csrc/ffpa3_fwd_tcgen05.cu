@@ -13,12 +13,15 @@
 //                     maxima swapped through shared memory; P (fp16) is written to SHARED memory, K-major, swizzled
 //   O^T += V_j^T P^T  cta_group::2, M = 256 (each CTA supplies 128 head-dim columns of V as an MN-major A operand straight
 //                     from the [keys, D] tile), N = 128 rows (each CTA supplies its 64 rows of P as the B operand), K = 256 keys
-// O^T's columns are the rows of BOTH CTAs, so the lazy-rescale factor of a row must reach the peer before the next PV.
-// Every tile each CTA writes its 64 factors (1.0 when the row max did not move) and a per-warp "moved" flag into both
-// CTAs' shared memory (st.shared::cluster, no waiting); the release on the p_full arrive publishes them.  The MMA thread
-// reads the flags after p_full(j): none set (the steady state) -> PV(j) is issued at once; any set -> it broadcasts
-// "rescale" on the decision barrier and waits until the softmax warps of both CTAs have scaled their lanes of O^T.  The
-// softmax warps look at decision(j-1) at the END of tile j, so no cross-CTA wait sits on the per-tile softmax chain.
+// O^T's columns are the rows of BOTH CTAs, so the lazy-rescale factor of a row must reach the peer before the next PV -
+// without a cluster-scope memory fence on the per-tile path (mbarrier.arrive.release.cluster = MEMBAR.ALL.GPU, 1-1.5 k
+// cycles per arrive, measured).  Every tile each row's factor (1.0 when the row max did not move) goes to both CTAs by
+// st.async, completing on the receiving CTA's decision barrier of that tile; each first-half-row warp sends its "moved"
+// flag to the leader the same way on p_full, with its arrive.  The MMA thread reads the flags after p_full(j): none set
+// (the steady state) -> PV(j) is issued at once; any set -> the verdict "rescale" goes out (st.async again, so a decision
+// barrier completes only when the verdict AND all 128 factors have landed) and it waits until the softmax warps of both
+// CTAs have scaled their lanes of O^T.  The softmax warps look at decision(j-1) at the END of tile j, so no cross-CTA
+// wait sits on the per-tile softmax chain.
 // The epilogue divides column c by the row sum l[c] (exchanged the same way) and stores O transposed.
 #include <cmath>
 
@@ -116,9 +119,9 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
   const uint32_t bar_q_full = bar_empty + 8 * MAX_STAGES;  // 1 (leader's)
   const uint32_t bar_s_full = bar_q_full + 8;              // 2 (each CTA, multicast commit)
   const uint32_t bar_s_free = bar_s_full + 16;             // 2 (leader's; 8 arrivals = 4 warps x 2 CTAs)
-  const uint32_t bar_p_full = bar_s_free + 16;             // 2 (leader's; 8 arrivals)
+  const uint32_t bar_p_full = bar_s_free + 16;             // 2 (leader's; 8 arrivals + 4 flag words by st.async)
   const uint32_t bar_pv_done = bar_p_full + 16;            // 2 (each CTA, multicast commit): P buffer b free / O^T stable
-  const uint32_t bar_decision = bar_pv_done + 16;          // 2 (each CTA; 1 arrival from the MMA thread): decision(j) is readable
+  const uint32_t bar_decision = bar_pv_done + 16;          // 2 (each CTA; 1 arrival + 516 bytes): verdict(j) and the 128 factors are readable
   const uint32_t bar_rsdone = bar_decision + 16;           // 1 (leader's; 8 arrivals): a requested rescale has been applied
   const uint32_t bar_o_full = bar_rsdone + 8;              // 1 (each CTA, multicast commit)
   const uint32_t tmem_slot = bar_o_full + 8;
@@ -474,7 +477,7 @@ ffpa3_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_
   if (warp == 2) tmem_dealloc<2>(tmem_base, ffpa3::TMEM_COLS);
 }
 
-// Host launcher, called from b200k_ffpa_fwd_f16 (ffpa_fwd_tcgen05.cu) for D = 256 / 512 when variant bit 0x200 is set.
+// Host launcher, called from b200k_ffpa_fwd_f16 (ffpa_fwd_tcgen05.cu): the default for D = 512, variant bit 0x200 for D = 256.
 int launch_ffpa_otrans(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N, int64_t D,
                        float scale, cudaStream_t s) {
   const uint64_t BH = uint64_t(B) * uint64_t(H);

@@ -91,6 +91,9 @@ int b200k_gemm_ex(const void* A, const void* B, void* C, int64_t M, int64_t N, i
  * variant: 0 = the shipped configuration.  Other values select experiment / fallback builds of the same math (piece
  *   counts, polynomial exp2 fraction, TMEM layout, 1-CTA vs CTA-pair FFPA, cycle trace); the bits are listed next to
  *   the dispatchers in csrc/fa2_fwd_tcgen05.cu and csrc/ffpa_fwd_tcgen05.cu.  Every build is parity-tested.
+ *   FFPA kernel selection: D = 512 runs the O^T kernel (csrc/ffpa3_fwd_tcgen05.cu: one pass over Q K^T per KV tile, like
+ *   the reference's ffpa_attn_templates_L1.cuh:L219-368); bit 0x400 keeps the D-sliced CTA-pair kernel there, bit 0x200
+ *   selects the O^T kernel at D = 256; every other D runs the D-sliced kernels (S recomputed per 256-column slice of O).
  */
 int b200k_fa2_fwd_f16(const void* Q, const void* K, const void* V, void* O, int64_t B, int64_t H, int64_t N,
                       int64_t D, float scale, int v_is_dn, int variant, void* stream);
