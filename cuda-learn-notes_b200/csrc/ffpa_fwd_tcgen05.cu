@@ -63,7 +63,8 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t tmem_slot = bar_o_full + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
   float* xch = reinterpret_cast<float*>(base_ptr + 1024);  // [2 tile parities][2 halves][128 rows] fp32 (SPLIT = 2)
-  const int nqk = D / CW;                                 // 64-wide chunks of the head dim
+  const int nqk = (D + CW - 1) / CW;                      // 64-wide chunks of the head dim; for D % 64 == 32 the last box is half
+                                                          // outside the tensor: TMA zero-fills it (adds 0 to S, 0-columns to O)
   const uint32_t smem_q = base + BAR_BYTES;               // resident Q: nqk boxes
   const uint32_t smem_ring = smem_q + (Q_RESIDENT ? nqk * BOX_BYTES : 0);
 
@@ -72,8 +73,8 @@ ffpa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int bh = blockIdx.z;
   const int q0 = blockIdx.x * BR;
   const int col0 = blockIdx.y * 256;                      // first output column of this slice
-  const int ncols = min(slice_cols, D - col0);            // 64 .. 256, multiple of 64
-  const int nv = ncols / CW;                              // V chunks in the slice
+  const int ncols = min(slice_cols, D - col0);            // 32 .. 256, multiple of 32
+  const int nv = (ncols + CW - 1) / CW;                   // V chunks in the slice (the TMA store clips a half-outside chunk)
   const int T = (N + BC - 1) / BC;
 
   if (threadIdx.x == 0) {
@@ -419,9 +420,9 @@ extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, v
   if (D == 32 || D == 64 || D == 96 || (D == 128 && !(variant & 16)))  // variant bit 16: run D=128 on this kernel (experiment)
     return b200k_fa2_fwd_f16(Q, K, V, O, B, H, N, D, scale, 0, variant, stream);
   if (!Q || !K || !V || !O) return set_error(B200K_EARG, "b200k_ffpa_fwd_f16: null pointer");
-  if (D < 128 || D > 1024 || (D % 64) != 0)
-    return set_error(B200K_EHEADDIM, "headdim not support! (b200k_ffpa_fwd_f16: D=%lld; supported 32/64/96/128 and 192..1024 step 64)",
-                     (long long)D);
+  // 160, 224, ... (D % 64 == 32) are the reference's ENABLE_FFPA_ALL_HEADDIM rungs (launch_templates.cuh:L483-552)
+  if (D < 128 || D > 1024 || (D % 32) != 0)
+    return set_error(B200K_EHEADDIM, "headdim not support! (b200k_ffpa_fwd_f16: D=%lld; supported 32 .. 1024 step 32)", (long long)D);
   if (B < 1 || H < 1 || N < 1 || N > INT32_MAX || B * H > 65535)
     return set_error(B200K_ESHAPE, "b200k_ffpa_fwd_f16: need B,H,N >= 1 and B*H <= 65535");
   if (scale <= 0.f) scale = 1.0f / sqrtf(float(D));
@@ -446,7 +447,7 @@ extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, v
   if ((rc = make_tmap_3d_u16(&tmV, V, BH, N, D, uint64_t(N) * D, D, 1, 128, 64, 128))) return rc;
   if ((rc = make_tmap_3d_u16(&tmO, O, BH, N, D, uint64_t(N) * D, D, 1, 32, 64, 128))) return rc;
   const bool q_resident = (D <= 512) && !(variant & 2);  // variant 2 forces the streaming-Q path (testing)
-  const int q_bytes = q_resident ? int(D / 64) * ffpa::BOX_BYTES : 0;
+  const int q_bytes = q_resident ? int((D + 63) / 64) * ffpa::BOX_BYTES : 0;
   int stages = (232448 - 1024 - ffpa::BAR_BYTES - q_bytes) / ffpa::STAGE_BYTES;
   if (stages > ffpa::MAX_STAGES) stages = ffpa::MAX_STAGES;
   const int smem = 1024 + ffpa::BAR_BYTES + q_bytes + stages * ffpa::STAGE_BYTES;

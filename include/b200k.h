@@ -84,7 +84,8 @@ int b200k_gemm_ex(const void* A, const void* B, void* C, int64_t M, int64_t N, i
  *   kernels/flash-attn/mma/basic/flash_attn_mma_share_qkv.cu:L833-886 (…_split_q_shared_qkv).
  *   v_is_dn = 1: V is passed transposed as [B,H,D,N] (the *_swizzle_qkv entry points, flash_attn_mma.py:L378).
  *
- * b200k_ffpa_fwd_f16 — large-headdim forward (FFPA L1), D in {256 .. 1024 step 64} (and the small D above).
+ * b200k_ffpa_fwd_f16 — large-headdim forward (FFPA L1), D in {160 .. 1024 step 32} (and the small D above); the
+ *   D % 64 == 32 rungs are the reference's ENABLE_FFPA_ALL_HEADDIM set (launch_templates.cuh:L483-552).
  *   Replaces ffpa_mma_acc_f16_L1 / ffpa_mma_acc_f32_L1, ffpa-attn-mma/csrc/pybind/ffpa_attn_api.cc:L8-17,
  *   launcher ffpa-attn-mma/csrc/cuffpa/launch_templates.cuh:L261-449.
  * scale <= 0 means 1/sqrt(D) (what both references hard-code).

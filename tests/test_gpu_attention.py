@@ -241,6 +241,27 @@ def test_ffpa_every_ladder_rung(D):
     assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), **TOL)
 
 
+@pytest.mark.parametrize("D", [160, 224, 288, 352, 480, 544, 736, 992])
+def test_ffpa_step32_head_dims(D):
+    """The reference's ENABLE_FFPA_ALL_HEADDIM rungs (ffpa-attn-mma/csrc/cuffpa/launch_templates.cuh:L483-552): head dims
+    that are multiples of 32 but not of 64.  The last 64-wide chunk of Q / K / V is half outside the tensor (TMA zero fill)
+    and the last chunk of O is clipped by the TMA store; memory after O's last row must stay untouched."""
+    from b200k import ops
+
+    torch.manual_seed(D)
+    N = 300
+    q, k, v = [torch.randn(1, 2, N, D, dtype=torch.half, device="cuda") for _ in range(3)]
+    buf = torch.full((1 * 2 * N * D + 4096,), 7.0, dtype=torch.half, device="cuda")
+    o = buf[:2 * N * D].view(1, 2, N, D)
+    ops.ffpa_fwd(q, k, v, o)
+    torch.cuda.synchronize()
+    assert torch.allclose(o.cpu().float(), oracle.attention(q, k, v).float(), **TOL)
+    assert bool((buf[2 * N * D:] == 7.0).all())
+    ones = torch.ones_like(v)
+    ops.ffpa_fwd(q, k, ones, o)
+    assert torch.allclose(o.float(), torch.ones_like(o).float(), atol=1e-3)
+
+
 @pytest.mark.parametrize("D", [256, 512])
 @pytest.mark.parametrize("N", [1, 63, 128, 255, 256, 257, 511, 1000, 2304])
 def test_ffpa_otrans_kernel_shapes(D, N):
