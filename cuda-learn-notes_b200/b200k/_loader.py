@@ -74,6 +74,7 @@ _SIGS = {
     "b200k_transpose_u16_batched": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "b200k_debug_set_trace": (c_int, [c_void_p]),
     "b200k_debug_set_hgemm_trace": (c_int, [c_void_p]),
+    "b200k_debug_hgemm_schedule": (c_int64, [c_int64, c_int, c_int, c_int, c_void_p, c_int64]),
     "b200k_activation": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "b200k_layer_norm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_float, c_int, c_int, c_void_p]),
     "b200k_dot_prod": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),

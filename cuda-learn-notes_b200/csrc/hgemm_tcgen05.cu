@@ -106,13 +106,15 @@ struct WorkItem {
   int last_writer;  // finisher: clusters (cluster_id, last_writer] hold the rest of this tile
 };
 
-__device__ __forceinline__ int sk_unit_begin(const GemmPlan& p, int c) { return c * p.units_lo + min(c, p.units_rem); }
-__device__ __forceinline__ int sk_unit_owner(const GemmPlan& p, int x) {
+// The schedule functions are host-callable too: b200k_debug_hgemm_schedule() replays them for tests/test_abi.py, which checks
+// coverage (every k-block of every tile exactly once) and the wait-for order (no cycle) over many shapes without a GPU.
+__host__ __device__ __forceinline__ int sk_unit_begin(const GemmPlan& p, int c) { return c * p.units_lo + (c < p.units_rem ? c : p.units_rem); }
+__host__ __device__ __forceinline__ int sk_unit_owner(const GemmPlan& p, int x) {
   const int big = p.units_rem * (p.units_lo + 1);
   return x < big ? x / (p.units_lo + 1) : p.units_rem + (x - big) / p.units_lo;
 }
 // i-th work item of cluster c (same sequence in the producer, the MMA issuer and the epilogue warps)
-__device__ __forceinline__ WorkItem get_work(const GemmPlan& p, int c, int G, int num_tiles, int num_kb, int i) {
+__host__ __device__ __forceinline__ WorkItem get_work(const GemmPlan& p, int c, int G, int num_tiles, int num_kb, int i) {
   WorkItem w;
   w.kind = -1;  // -1: no more work
   int n_sk = 0;
@@ -120,7 +122,7 @@ __device__ __forceinline__ WorkItem get_work(const GemmPlan& p, int c, int G, in
     const int ub = sk_unit_begin(p, c), ue = sk_unit_begin(p, c + 1);
     if (ub < ue) {
       const int j0 = ub / num_kb, k0 = ub - j0 * num_kb;
-      const int k1 = min(num_kb, k0 + (ue - ub));
+      const int k1 = (k0 + (ue - ub) < num_kb) ? k0 + (ue - ub) : num_kb;
       const bool two = ue > (j0 + 1) * num_kb;
       n_sk = two ? 2 : 1;
       if (i < n_sk) {
@@ -528,6 +530,21 @@ static int get_sk_workspace(int device, cudaStream_t stream, size_t partial_byte
   return B200K_OK;
 }
 
+// Decides whether the remainder round of this problem runs stream-K and, if so, fills the schedule part of the plan
+// (sk_tiles, units_lo, units_rem); the caller then runs max_clusters clusters and attaches the workspace.
+static bool plan_stream_k(int nacc, int64_t num_tiles, int num_kb, int max_clusters, int tune, GemmPlan* plan) {
+  const int64_t rem_tiles = num_tiles % max_clusters;
+  const bool force_sk = ((tune >> 22) & 1) != 0;   // experiments: stream-K also for a single partial round
+  if (!(nacc == 2 && rem_tiles != 0 && (num_tiles > max_clusters || force_sk) && num_kb >= 8 && max_clusters <= 128 &&
+        !((tune >> 20) & 1)))
+    return false;
+  const int64_t units = rem_tiles * num_kb;
+  plan->sk_tiles = int(rem_tiles);
+  plan->units_lo = int(units / max_clusters);
+  plan->units_rem = int(units % max_clusters);
+  return true;
+}
+
 template <class Cfg>
 static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
                         const DeviceInfo& di, int tune) {
@@ -550,22 +567,15 @@ static int launch_hgemm(const void* A, const void* B, void* C, int64_t M, int64_
   GemmPlan plan;
   plan.trace = g_hgemm_trace;
   const int num_kb = int((K + Cfg::BK - 1) / Cfg::BK);
-  const int64_t rem_tiles = num_tiles % max_clusters;
   // Only when at least one data-parallel round follows: the finisher's fix-up (wait for the writers, read their partials
   // back from L2) then runs under the next tile's main loop.  With nothing to hide behind it costs more than it saves
   // (2048^3, 64 tiles on 74 pairs: 27.3 us stream-K vs 19.0 us plain, measured).
   // Not with MT = 2 either: a single accumulator buffer means the finisher's fix-up stalls the MMA stream (8192^3:
   // 701 us with the remainder round stream-K, 677 us without - ncu, profiles/r02_hgemm_tile_sweep_ncu.txt).
-  const bool force_sk = ((tune >> 22) & 1) != 0;   // experiments: stream-K also for a single partial round
-  if (Cfg::NACC == 2 && rem_tiles != 0 && (num_tiles > max_clusters || force_sk) && num_kb >= 8 && max_clusters <= 128 &&
-      !((tune >> 20) & 1)) {
-    const int64_t units = rem_tiles * num_kb;
+  if (plan_stream_k(Cfg::NACC, num_tiles, num_kb, max_clusters, tune, &plan)) {
     SkWorkspace ws;
     if ((rc = get_sk_workspace(di.device, stream, size_t(max_clusters) * Cfg::CG * Cfg::BM_CTA * Cfg::BN * sizeof(float), &ws))) return rc;
     clusters = max_clusters;
-    plan.sk_tiles = int(rem_tiles);
-    plan.units_lo = int(units / clusters);
-    plan.units_rem = int(units % clusters);
     plan.partials = ws.partials;
     plan.flags = ws.flags;
   }
@@ -668,6 +678,31 @@ static int gemm_dispatch(const char* who, const void* A, const void* B, void* C,
 extern "C" int b200k_debug_set_hgemm_trace(void* dev_u64_buffer) {
   b200k::g_hgemm_trace = static_cast<unsigned long long*>(dev_u64_buffer);
   return B200K_OK;
+}
+
+// Debug hook (host only, no device needed): the work-item schedule the 256 x 256 pair kernel would run for `num_tiles` output
+// tiles of `num_kb` k-blocks on `clusters` resident CTA pairs - the same plan_stream_k() / get_work() the launcher and the
+// kernel use.  Rows of 7 int32: cluster, item index, tile, kb0, kb1, kind (0 whole tile, 1 writer, 2 finisher),
+// last_writer.  Returns the number of rows (also when it exceeds `cap`; only `cap` rows are written), < 0 on bad arguments.
+extern "C" int64_t b200k_debug_hgemm_schedule(int64_t num_tiles, int num_kb, int clusters, int tune, int32_t* rows, int64_t cap) {
+  using namespace b200k;
+  if (num_tiles < 1 || num_tiles > INT32_MAX || num_kb < 1 || clusters < 1 || (!rows && cap > 0)) return -1;
+  GemmPlan plan;
+  const bool sk = plan_stream_k(2, num_tiles, num_kb, clusters, tune, &plan);
+  const int G = sk ? clusters : int(num_tiles < clusters ? num_tiles : clusters);
+  int64_t n = 0;
+  for (int c = 0; c < G; ++c) {
+    for (int i = 0;; ++i) {
+      const WorkItem w = get_work(plan, c, G, int(num_tiles), num_kb, i);
+      if (w.kind < 0) break;
+      if (n < cap) {
+        int32_t* r = rows + n * 7;
+        r[0] = c; r[1] = i; r[2] = w.tile; r[3] = w.kb0; r[4] = w.kb1; r[5] = w.kind; r[6] = w.last_writer;
+      }
+      ++n;
+    }
+  }
+  return n;
 }
 
 extern "C" int b200k_hgemm_f16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int b_is_nk,

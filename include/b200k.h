@@ -203,6 +203,11 @@ int b200k_transpose_u16_batched(const void* x, void* y, int64_t batch, int64_t M
 int b200k_debug_set_trace(void* dev_u64_buffer);
 /* Debug hook of the GEMM kernel: 128 uint64 %globaltimer stamps per cluster (see hgemm_tcgen05.cu); NULL switches it off. */
 int b200k_debug_set_hgemm_trace(void* dev_u64_buffer);
+/* Debug hook, host only (runs without a GPU): the stream-K work-item schedule of the 256 x 256 pair GEMM for `num_tiles`
+ * tiles of `num_kb` k-blocks on `clusters` CTA pairs, as rows of 7 int32 {cluster, item, tile, kb0, kb1, kind, last_writer}
+ * (kind 0 = whole tile, 1 = writer of partial sums, 2 = finisher); returns the row count.  tests/test_abi.py checks coverage
+ * and the wait-for order with it. */
+int64_t b200k_debug_hgemm_schedule(int64_t num_tiles, int num_kb, int clusters, int tune, int32_t* rows, int64_t cap);
 
 #ifdef __cplusplus
 }
