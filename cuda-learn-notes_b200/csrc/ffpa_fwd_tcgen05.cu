@@ -434,8 +434,8 @@ extern "C" int b200k_ffpa_fwd_f16(const void* Q, const void* K, const void* V, v
   // CTA-pair kernel for D = 512 / 768 / 1024 (measured on (1,32,4096,D): D=512 994 vs 836 TFLOP/s; at D=256 the
   // single-CTA kernel is ahead, 1.21 vs 1.16 PFLOP/s — profiles/r01_ffpa_check.jsonl); variant bit 8 forces it.
   // D = 512 (BASELINE config #4): the O^T kernel (ffpa3_fwd_tcgen05.cu), which computes S once per KV tile instead of once
-  // per 256-column slice of O: 1093 vs 982 TFLOP/s on (1,32,4096,512).  Variant bit 0x200 forces it (also for D = 256, where
-  // the S-recompute-free single-CTA kernel is faster: 1372 vs 798), bit 0x400 keeps the D-sliced pair kernel at D = 512.
+  // per 256-column slice of O: 1.40 vs 0.93-1.01 PFLOP/s on (1,32,4096,512).  Variant bit 0x200 forces it (also for D = 256,
+  // where the S-recompute-free single-CTA kernel is faster: 1.32-1.40 vs 1.11), bit 0x400 keeps the D-sliced pair kernel.
   if (((variant & 0x200) && (D == 256 || D == 512)) || (D == 512 && !(variant & (0x400 | 7 | 8))))
     return launch_ffpa_otrans(Q, K, V, O, B, H, N, D, scale, s);
   if ((D % 256) == 0 && (D >= 512 || (variant & 8)) && !(variant & 7))
